@@ -1,0 +1,204 @@
+/* b2j.h - C ABI of libb2j.so, the B200 (sm_100a) baseline-JPEG encode path.
+ *
+ * This is the drop-in boundary.  The reference (LiteJPEG) has no FFI of its
+ * own: its operator API is "a class with .sink/.source whose behaviour a bench
+ * observes as Packet(list[int]) in -> list[int] out" (test/new_zigzag_tb.py:22-51
+ * of the reference).  Each entry point below replaces the datapath of one such
+ * operator, or of the software model function with the same job; the citation
+ * after "replaces:" is the reference interface, relative to /root/reference.
+ * INTEGRATION.md shows the ctypes stub a maintainer would add per bench.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; no C++/torch types;
+ *   - every `*_dev` / unmarked data pointer is caller-allocated DEVICE memory on
+ *     the current CUDA device; `*_host` pointers are host memory; quantisation
+ *     tables are 64-entry HOST arrays in natural (row-major) order, read at call
+ *     time and passed by value to the kernel;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); work is
+ *     asynchronous on that stream unless stated; the library keeps no global
+ *     mutable state, so calls are re-entrant, one stream per caller thread;
+ *   - return value: 0 = OK, < 0 = argument error (B2J_E_*), > 0 = cudaError_t;
+ *     never throws, never aborts.  b2j_last_error() gives a message for the
+ *     calling thread.
+ */
+#ifndef B2J_H
+#define B2J_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2J_OK 0
+#define B2J_E_ARG (-1)        /* null pointer, bad enum, negative size */
+#define B2J_E_SHAPE (-2)      /* unsupported geometry (e.g. side > 65535) */
+#define B2J_E_WORKSPACE (-3)  /* workspace too small */
+#define B2J_E_CAPACITY (-4)   /* output slot too small for a frame (sizes[] holds the need, negated) */
+#define B2J_E_ALIGN (-5)      /* a pointer that must be 16-byte aligned is not */
+
+#define B2J_SUB_444 444
+#define B2J_SUB_422 422
+#define B2J_SUB_420 420
+
+/* ZRL policy of the run-length stage */
+#define B2J_ZRL_EAGER 0     /* gateware rule, litejpeg/core/rle/rlecore.py:101-105 */
+#define B2J_ZRL_STANDARD 1  /* T.81 / libjpeg rule: ZRL only in front of a non-zero */
+
+/* colour model of b2j_rgb2ycbcr */
+#define B2J_CSC_JFIF 0      /* software model, test/model/enc_frame.py:27-35 */
+#define B2J_CSC_XAPP930 1   /* gateware, litejpeg/core/csc.py:85-160 (coef_w = 8) */
+
+/* rounding of b2j_quantize */
+#define B2J_Q_ROUND 0       /* model, test/model/enc_frame.py:111-129 (half away from zero) */
+#define B2J_Q_TRUNC 1       /* older model, test/model/encoder.py:84-88 (int(v/d)) */
+#define B2J_Q_RECIPROCAL 2  /* gateware, litejpeg/core/quantization.py:124-168 */
+
+/* variant of b2j_fused_block */
+#define B2J_FUSED_AUTO 0    /* tiled kernel when the layout allows, else simple */
+#define B2J_FUSED_SIMPLE 1  /* one thread per 8x8 block, any geometry */
+#define B2J_FUSED_TILED 2   /* shared-memory tiled, bulk-async loads; needs 16-byte aligned rows */
+
+/* A batch of equally sized, interleaved 8-bit RGB frames (H x W x 3, like the
+ * array the model reads at test/model/enc_frame.py:7-10). */
+typedef struct b2j_image_desc {
+    int32_t width;          /* source pixels, 1..65535 */
+    int32_t height;         /* source pixels, 1..65535 */
+    int32_t subsampling;    /* B2J_SUB_* */
+    int32_t n_frames;       /* >= 1 */
+    int64_t row_stride;     /* bytes between rows, >= 3*width (0 = packed) */
+    int64_t frame_stride;   /* bytes between frames, >= height*row_stride (0 = packed) */
+} b2j_image_desc;
+
+/* Derived geometry (what the scan order and buffer sizes follow from). */
+typedef struct b2j_geometry {
+    int32_t h, v;                 /* luma sampling factors */
+    int32_t mcus_x, mcus_y;       /* MCUs per row / column */
+    int32_t blocks_per_mcu;       /* h*v + 2 */
+    int32_t padded_width, padded_height;
+    int64_t blocks_per_frame;     /* mcus_x*mcus_y*blocks_per_mcu */
+    int32_t header_bytes;         /* SOI..SOS length written in front of the scan */
+    int32_t reserved;
+} b2j_geometry;
+
+const char *b2j_version(void);
+/* Copies the calling thread's last error message; returns its length. */
+size_t b2j_last_error(char *buf, size_t cap);
+int b2j_get_geometry(const b2j_image_desc *desc, b2j_geometry *geo);
+/* [ext] IJG scaling of the Annex-K tables; quality 85 gives the model's tables
+ * (test/model/enc_frame.py:141-159), 50 the gateware's (core/quantization.py:20-27). */
+int b2j_quant_tables(int quality, uint8_t qy_host[64], uint8_t qc_host[64]);
+
+/* ---------------------------------------------------------------- K0: one kernel per stage operator */
+
+/* replaces: RGB2YCbCr datapath, litejpeg/core/csc.py:41-160 (mode XAPP930) and
+ * rgb2ycbcr, test/model/enc_frame.py:27-35 (mode JFIF).  rgb: n_pixels x 3
+ * interleaved; y/cb/cr: n_pixels each. */
+int b2j_rgb2ycbcr(const uint8_t *rgb, uint8_t *y, uint8_t *cb, uint8_t *cr,
+                  int64_t n_pixels, int mode, void *stream);
+
+/* replaces: YCbCr444to422 datapath, litejpeg/core/crs.py:8-65.  Streams of
+ * n_pixels (even); cb_cr carries mean(Cb) on even and mean(Cr) on odd pixels. */
+int b2j_ycbcr444to422(const uint8_t *y, const uint8_t *cb, const uint8_t *cr,
+                      uint8_t *y_out, uint8_t *cb_cr_out, int64_t n_pixels, void *stream);
+
+/* [ext] plane subsampling with the same pair mean, horizontally (422) and then
+ * vertically (420).  in: height x width, out: (height/v) x (width/2). */
+int b2j_chroma_subsample(const uint8_t *in, uint8_t *out, int32_t height, int32_t width,
+                         int32_t subsampling, void *stream);
+
+/* replaces: DCT, litejpeg/core/new_dct6.py:400-525 (operator surface) with the
+ * arithmetic of dct, test/model/enc_frame.py:42-109 (float64 graph, int(v/8)).
+ * in: n_blocks x 64 samples 0..255, row-major; out: n_blocks x 64, [v][u]. */
+int b2j_dct(const int16_t *in, int16_t *out, int64_t n_blocks, void *stream);
+
+/* replaces: Quantization, litejpeg/core/quantization.py:29-182 and quantize,
+ * test/model/enc_frame.py:111-129. */
+int b2j_quantize(const int16_t *in, int16_t *out, int64_t n_blocks,
+                 const uint8_t table_host[64], int mode, void *stream);
+
+/* replaces: ZigZag, litejpeg/core/zigzag.py:37-212 and zigzag, enc_frame.py:161-165. */
+int b2j_zigzag(const int16_t *in, int16_t *out, int64_t n_blocks, void *stream);
+
+/* replaces: RunLength, litejpeg/core/rle/rlecore.py:30-146.  in: n_blocks x 64
+ * zig-zag ordered blocks of ONE component in scan order; prev_dc seeds the DC
+ * predictor.  words: n_blocks x 64 slots, amp[0:12] run[12:16] valid[16]. */
+int b2j_run_length(const int16_t *in, uint32_t *words, int64_t n_blocks, int32_t prev_dc,
+                   void *stream);
+
+/* replaces: EntropyCoder, litejpeg/core/rle/entropycoder.py:19-65: size = bit
+ * length of |x|. */
+int b2j_entropy_size(const int16_t *in, uint8_t *size, int64_t n, void *stream);
+
+/* replaces: RLEMain, litejpeg/core/rle/rlemain.py:24-80: amp[0:12] size[12:16]
+ * run[16:20] valid[20]; size is that of the input coefficient of the slot. */
+int b2j_rle_main(const int16_t *in, uint32_t *words, int64_t n_blocks, int32_t prev_dc,
+                 void *stream);
+
+/* ---------------------------------------------------------------- K1..K4: the fused encode path */
+
+/* K1.  replaces: the loop body test/model/enc_frame.py:203-217
+ * (rgb2ycbcr -> dct -> quantize -> zigzag per block) plus [ext] chroma
+ * subsampling and edge replication.  coefs: n_frames x blocks_per_frame x 64
+ * int16, zig-zag order, blocks in scan (MCU-interleaved) order, DC not yet
+ * differenced.  coefs must be 16-byte aligned. */
+int b2j_fused_block(const uint8_t *rgb, const b2j_image_desc *desc,
+                    const uint8_t qy_host[64], const uint8_t qc_host[64],
+                    int16_t *coefs, int variant, void *stream);
+
+/* K2.  replaces: DC differencing enc_frame.py:219-230, RunLength
+ * rlecore.py:84-132, EntropyCoder entropycoder.py:55-65, and [ext] the Annex-K
+ * code-length lookup.  bits: n_frames x blocks_per_frame Huffman-coded sizes. */
+int b2j_block_bits(const int16_t *coefs, const b2j_image_desc *desc, int zrl,
+                   int32_t *bits, void *stream);
+
+/* K3.  [ext] exclusive prefix sum of bits within each frame.
+ * offsets: n_frames x blocks_per_frame; total_bits: n_frames.
+ * workspace: b2j_scan_workspace_bytes(desc) bytes. */
+size_t b2j_scan_workspace_bytes(const b2j_image_desc *desc);
+int b2j_scan(const int32_t *bits, const b2j_image_desc *desc, uint32_t *offsets,
+             int64_t *total_bits, void *workspace, void *stream);
+
+/* K4.  replaces: huffman, enc_frame.py:179-180 (an identity stub) and the
+ * header sketch :189-200; [ext] Annex-K Huffman codes at the scanned offsets,
+ * MSB-first packing, 1-padding, 0xFF00 stuffing, JFIF header and EOI.
+ * out: n_frames slots of out_cap bytes; sizes[f] = bytes of frame f, or minus
+ * the bytes needed when out_cap is too small (then the call returns
+ * B2J_E_CAPACITY after a stream synchronise only if check_sizes_host != 0). */
+size_t b2j_bitpack_workspace_bytes(const b2j_image_desc *desc, int64_t out_cap);
+int b2j_bitpack(const int16_t *coefs, const uint32_t *offsets, const int64_t *total_bits,
+                const b2j_image_desc *desc, const uint8_t qy_host[64], const uint8_t qc_host[64],
+                int zrl, void *workspace, uint8_t *out, int64_t out_cap, int64_t *sizes,
+                void *stream);
+
+/* The whole path K1..K4 on device buffers.  workspace: b2j_encode_workspace_bytes().
+ * quality 1..100 picks the [ext] IJG tables, or pass quality = 0 and explicit
+ * tables. */
+size_t b2j_encode_workspace_bytes(const b2j_image_desc *desc, int64_t out_cap);
+int64_t b2j_default_out_cap(const b2j_image_desc *desc);
+int b2j_encode(const uint8_t *rgb, const b2j_image_desc *desc, int quality,
+               const uint8_t qy_host[64], const uint8_t qc_host[64], int zrl,
+               void *workspace, size_t workspace_bytes,
+               uint8_t *out, int64_t out_cap, int64_t *sizes, void *stream);
+
+/* Number of kernel launches b2j_encode issues for this geometry. */
+int b2j_encode_launch_count(const b2j_image_desc *desc);
+
+/* ---------------------------------------------------------------- host-buffer encoder (end-to-end)
+ * Owns its device workspace, pinned staging buffers and streams (the only
+ * entry points that allocate).  encode_host: rgb_host -> JFIF files in
+ * out_host (n_frames slots of out_cap bytes), sizes_host[n_frames].  Copies
+ * and kernels of consecutive frame chunks overlap; the call returns when the
+ * last byte is in out_host. */
+typedef struct b2j_encoder b2j_encoder;
+int b2j_encoder_create(b2j_encoder **enc, const b2j_image_desc *desc, int quality, int zrl,
+                       int64_t out_cap, int32_t frames_per_chunk);
+int b2j_encoder_encode_host(b2j_encoder *enc, const uint8_t *rgb_host, int32_t n_frames,
+                            uint8_t *out_host, int64_t *sizes_host);
+int b2j_encoder_destroy(b2j_encoder *enc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2J_H */

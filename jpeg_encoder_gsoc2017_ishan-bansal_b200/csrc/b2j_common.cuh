@@ -1,0 +1,85 @@
+// Shared declarations of libb2j: error plumbing, geometry, constant tables.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/b2j.h"
+
+namespace b2j {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define B2J_CUDA(call)                                                        \
+    do {                                                                      \
+        cudaError_t e__ = (call);                                             \
+        if (e__ != cudaSuccess) return ::b2j::cuda_fail(e__, #call);          \
+    } while (0)
+
+#define B2J_REQUIRE(cond, code, ...)                                          \
+    do {                                                                      \
+        if (!(cond)) { ::b2j::set_error(__VA_ARGS__); return (code); }        \
+    } while (0)
+
+#define B2J_LAUNCH_CHECK(name)                                                \
+    do {                                                                      \
+        cudaError_t e__ = cudaGetLastError();                                 \
+        if (e__ != cudaSuccess) return ::b2j::cuda_fail(e__, name);           \
+    } while (0)
+
+// ---------------------------------------------------------------- geometry
+struct Geo {
+    int width, height;            // source pixels
+    int h, v;                     // luma sampling factors
+    int mcu_w, mcu_h;             // MCU size in pixels
+    int mcus_x, mcus_y;
+    int bpm;                      // blocks per MCU
+    int n_frames;
+    long long row_stride, frame_stride;   // bytes
+    long long blocks_per_frame;
+};
+
+int make_geo(const b2j_image_desc *d, Geo *g);
+
+static const int kHeaderBytes = 623;   // SOI APP0 DQTx2 SOF0 DHTx4 SOS
+
+// Quantisation multipliers for the fused kernel: q = (|c| * mul + 2^19) >> 20
+// reproduces round-half-away(|c| / d) for every |c| <= 1024, d in 1..255
+// (checked exhaustively in tests/test_host_math.py through csrc/host_check).
+struct QuantMul {
+    uint32_t mul[2][64];          // [luma|chroma][natural index]
+};
+void make_quant_mul(const uint8_t *qy, const uint8_t *qc, QuantMul *qm);
+
+// ---------------------------------------------------------------- tables (host + device)
+// Zig-zag position of natural index i (enc_frame.py:131-139 / zigzag.py:19-27).
+#define B2J_ZIGZAG_INIT                                                         \
+    { 0, 1, 5, 6, 14, 15, 27, 28, 2, 4, 7, 13, 16, 26, 29, 42,                 \
+      3, 8, 12, 17, 25, 30, 41, 43, 9, 11, 18, 24, 31, 40, 44, 53,             \
+      10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38, 46, 51, 55, 60,          \
+      21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63 }
+
+extern const uint8_t kZigzag[64];          // natural index -> zig-zag position
+extern const uint8_t kBaseLuma[64];        // Annex K.1
+extern const uint8_t kBaseChroma[64];      // Annex K.2
+
+// Annex K.3 typical Huffman tables (BITS, HUFFVAL)
+extern const uint8_t kDcLumaBits[16], kDcChromaBits[16], kDcVals[12];
+extern const uint8_t kAcLumaBits[16], kAcChromaBits[16], kAcLumaVals[162], kAcChromaVals[162];
+
+// Device-side code tables: entry = (length << 16) | code.
+struct HuffLut {
+    uint32_t dc[2][16];           // [luma|chroma][size category]
+    uint32_t ac[2][256];          // [luma|chroma][(run << 4) | size]
+};
+const HuffLut &host_huff_lut();
+
+int jfif_header(const Geo &g, const uint8_t *qy, const uint8_t *qc, uint8_t *out /* >= kHeaderBytes */);
+
+static inline void *as_ptr(void *p) { return p; }
+static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace b2j

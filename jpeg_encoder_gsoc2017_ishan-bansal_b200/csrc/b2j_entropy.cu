@@ -1,0 +1,519 @@
+// K2..K4: run-length + Huffman symbol sizes per block, per-frame exclusive scan
+// of bit offsets, parallel bit packing, 0xFF byte stuffing, JFIF framing.
+//
+// Symbol rules (the only JPEG-style RLE in the reference is gateware):
+//   DC: diff against the previous block of the same component, predictor 0 at
+//       the start of a frame, never reset (test/model/enc_frame.py:202,219-230;
+//       litejpeg/core/rle/rlecore.py:86-98);
+//   AC: (run, amplitude) pairs; B2J_ZRL_EAGER emits (15,0) on every 16th
+//       consecutive zero and (0,0) when index 63 is a zero that did not just
+//       complete a ZRL (rlecore.py:101-114); B2J_ZRL_STANDARD is T.81 F.1.2.2;
+//   size = bit length of |x| (litejpeg/core/rle/entropycoder.py:55-65).
+// Everything after the symbols is [ext] (the reference's huffman() is an
+// identity stub, enc_frame.py:179-180): Annex-K codes, additional bits
+// (x > 0 ? x : x - 1), MSB-first packing, 1-padding, 0xFF -> 0xFF00, header, EOI.
+//
+// The same block walker produces the sizes (K2) and the bits (K4), so scanned
+// offsets and emitted lengths cannot disagree.
+#include "b2j_common.cuh"
+#include "b2j_math.cuh"
+
+namespace b2j {
+
+struct EGeo {
+    int hv, bpm;                  // luma blocks per MCU, blocks per MCU
+    int n_frames;
+    long long nblk;               // blocks per frame
+};
+
+static EGeo egeo_of(const Geo &g)
+{
+    EGeo e;
+    e.hv = g.h * g.v; e.bpm = g.bpm; e.n_frames = g.n_frames; e.nblk = g.blocks_per_frame;
+    return e;
+}
+
+struct LutParam { HuffLut lut; };
+
+__device__ __forceinline__ void load_lut(const LutParam &L, uint32_t *s_dc /*[2][16]*/, uint32_t *s_ac /*[2][256]*/)
+{
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) s_dc[i] = L.lut.dc[i >> 4][i & 15];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_ac[i] = L.lut.ac[i >> 8][i & 255];
+}
+
+// DC of the previous block of the same component inside the frame (0 if none).
+__device__ __forceinline__ int prev_dc(const int16_t *frame_coefs, long long b, const EGeo &e)
+{
+    const int k = (int)(b % e.bpm);
+    long long p;
+    if (k < e.hv) p = k > 0 ? b - 1 : b - e.bpm + e.hv - 1;
+    else p = b - e.bpm;
+    return p >= 0 ? (int)frame_coefs[p * 64] : 0;
+}
+
+// Walks one block in zig-zag order and hands every coded field to sink.put(value, nbits).
+template <bool EAGER, class Sink>
+__device__ __forceinline__ void walk_block(const int16_t *__restrict__ c, int diff, const uint32_t *__restrict__ lut_dc,
+                                           const uint32_t *__restrict__ lut_ac, Sink &sink)
+{
+    {
+        const int s = bit_size(diff);
+        const uint32_t e = lut_dc[s];
+        const uint32_t extra = (uint32_t)(diff < 0 ? diff - 1 : diff) & ((1u << s) - 1u);
+        sink.put(((e & 0xFFFFu) << s) | extra, (int)(e >> 16) + s);
+    }
+    const uint32_t zrl = lut_ac[0xF0], eob = lut_ac[0x00];
+    int run = 0;
+    const uint4 *c4 = reinterpret_cast<const uint4 *>(c);
+#pragma unroll 1
+    for (int i = 0; i < 8; i++) {
+        const uint4 q = __ldg(c4 + i);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int k = i * 8 + j;
+            if (k == 0) continue;
+            const int v = (int)(int16_t)(w[j >> 1] >> (16 * (j & 1)));
+            uint32_t val = 0u;
+            int len = 0;
+            if (v != 0) {
+                if (!EAGER) {
+                    while (run > 15) { sink.put(zrl & 0xFFFFu, (int)(zrl >> 16)); run -= 16; }
+                }
+                const int s = bit_size(v);
+                const uint32_t e = lut_ac[(run << 4) | s];
+                val = ((e & 0xFFFFu) << s) | ((uint32_t)(v < 0 ? v - 1 : v) & ((1u << s) - 1u));
+                len = (int)(e >> 16) + s;
+                run = 0;
+            } else if (EAGER && run == 15) {
+                val = zrl & 0xFFFFu; len = (int)(zrl >> 16); run = 0;
+            } else if (k == 63) {
+                val = eob & 0xFFFFu; len = (int)(eob >> 16);
+            } else {
+                run++;
+            }
+            sink.put(val, len);
+        }
+    }
+}
+
+struct CountSink {
+    int bits;
+    __device__ __forceinline__ void put(uint32_t, int len) { bits += len; }
+};
+
+// ---------------------------------------------------------------- K2
+template <bool EAGER>
+__global__ void __launch_bounds__(128) k_block_bits(const int16_t *__restrict__ coefs, int32_t *__restrict__ bits, EGeo e,
+                                                    const __grid_constant__ LutParam L)
+{
+    __shared__ uint32_t s_dc[32], s_ac[512];
+    load_lut(L, s_dc, s_ac);
+    __syncthreads();
+    const long long total = e.nblk * e.n_frames;
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    const long long f = g / e.nblk, b = g % e.nblk;
+    const int16_t *fc = coefs + f * e.nblk * 64;
+    const int16_t *c = fc + b * 64;
+    const int chroma = (int)(b % e.bpm) >= e.hv;
+    CountSink sink{0};
+    walk_block<EAGER>(c, (int)c[0] - prev_dc(fc, b, e), s_dc + 16 * chroma, s_ac + 256 * chroma, sink);
+    bits[g] = sink.bits;
+}
+
+// ---------------------------------------------------------------- K3 (three small kernels)
+constexpr int kScanChunk = 1024;          // blocks per scan chunk (256 threads x 4)
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v)
+{
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t n = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += n;
+    }
+    return v;
+}
+
+// exclusive scan over the CTA (256 threads); returns exclusive prefix, *total = CTA sum
+__device__ __forceinline__ uint32_t cta_excl_scan_256(uint32_t v, uint32_t *s_warp /*[8]*/, uint32_t *total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t inc = warp_incl_scan(v);
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        const uint32_t x = s_warp[w];
+        if (w < warp) base += x;
+        tot += x;
+    }
+    __syncthreads();
+    *total = tot;
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(256) k_chunk_sums(const int32_t *__restrict__ bits, uint32_t *__restrict__ partial,
+                                                    long long nblk, int chunks)
+{
+    __shared__ uint32_t s_warp[8];
+    const int f = blockIdx.y, ch = blockIdx.x;
+    const int32_t *p = bits + (long long)f * nblk;
+    uint32_t v = 0;
+    for (int i = 0; i < 4; i++) {
+        long long b = (long long)ch * kScanChunk + i * 256 + threadIdx.x;
+        if (b < nblk) v += (uint32_t)p[b];
+    }
+    uint32_t tot;
+    cta_excl_scan_256(v, s_warp, &tot);
+    if (threadIdx.x == 0) partial[(long long)f * chunks + ch] = tot;
+}
+
+// one CTA per frame: partial[] becomes the exclusive prefix; total_bits[f] the frame sum
+__global__ void __launch_bounds__(256) k_scan_partials(uint32_t *__restrict__ partial, int64_t *__restrict__ total_bits, int chunks)
+{
+    __shared__ uint32_t s_warp[8];
+    uint32_t *p = partial + (long long)blockIdx.x * chunks;
+    unsigned long long carry = 0;
+    for (int base = 0; base < chunks; base += 256) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = i < chunks ? p[i] : 0u;
+        uint32_t tot;
+        const uint32_t ex = cta_excl_scan_256(v, s_warp, &tot);
+        if (i < chunks) p[i] = (uint32_t)carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) total_bits[blockIdx.x] = (int64_t)carry;
+}
+
+__global__ void __launch_bounds__(256) k_scan_apply(const int32_t *__restrict__ bits, const uint32_t *__restrict__ partial,
+                                                    uint32_t *__restrict__ offsets, long long nblk, int chunks)
+{
+    __shared__ uint32_t s_warp[8];
+    const int f = blockIdx.y, ch = blockIdx.x;
+    const int32_t *p = bits + (long long)f * nblk;
+    uint32_t *o = offsets + (long long)f * nblk;
+    // thread t owns 4 consecutive blocks so that the scan order is the block order
+    const long long b0 = (long long)ch * kScanChunk + threadIdx.x * 4;
+    uint32_t v[4], sum = 0;
+    for (int i = 0; i < 4; i++) { v[i] = b0 + i < nblk ? (uint32_t)p[b0 + i] : 0u; sum += v[i]; }
+    uint32_t tot;
+    uint32_t ex = cta_excl_scan_256(sum, s_warp, &tot) + partial[(long long)f * chunks + ch];
+    for (int i = 0; i < 4; i++) {
+        if (b0 + i < nblk) o[b0 + i] = ex;
+        ex += v[i];
+    }
+}
+
+// ---------------------------------------------------------------- K4a: bit packing (unstuffed)
+constexpr int kPackBlocks = 128;                    // blocks per CTA
+constexpr int kLook = 8;                            // lookahead blocks (>= 31 bits / 4 bits per smallest block)
+constexpr int kStageWords = ((kPackBlocks + kLook) * 1728 + 31) / 32 + 4;
+
+struct PackSink {
+    uint32_t *stage;              // shared staging words, zeroed
+    unsigned long long acc;
+    int nbits;                    // valid low bits of acc
+    int widx;                     // next staging word
+    __device__ __forceinline__ void begin(uint32_t *s, uint32_t bitpos)
+    {
+        stage = s; acc = 0ull; nbits = (int)(bitpos & 31u); widx = (int)(bitpos >> 5);
+    }
+    __device__ __forceinline__ void put(uint32_t val, int len)
+    {
+        acc = (acc << len) | val;
+        nbits += len;
+        if (nbits >= 32) {
+            atomicOr(stage + widx, (uint32_t)(acc >> (nbits - 32)));
+            widx++;
+            nbits -= 32;
+        }
+    }
+    __device__ __forceinline__ void finish()
+    {
+        if (nbits > 0) atomicOr(stage + widx, (uint32_t)(acc << (32 - nbits)));
+    }
+};
+
+// grid: (chunks_per_frame, n_frames).  unstuffed: n_frames slots of ucap bytes
+// (ucap multiple of 4), big-endian bit order, padded with 1s to a whole byte.
+template <bool EAGER>
+__global__ void __launch_bounds__(kPackBlocks) k_bitpack(const int16_t *__restrict__ coefs, const uint32_t *__restrict__ offsets,
+                                                         const int64_t *__restrict__ total_bits, uint8_t *__restrict__ unstuffed,
+                                                         long long ucap, EGeo e, const __grid_constant__ LutParam L)
+{
+    __shared__ uint32_t s_dc[32], s_ac[512];
+    __shared__ uint32_t s_stage[kStageWords];
+    load_lut(L, s_dc, s_ac);
+    const int f = blockIdx.y;
+    const long long b0 = (long long)blockIdx.x * kPackBlocks;
+    const long long b1 = min(b0 + kPackBlocks, e.nblk);
+    const int16_t *fc = coefs + (long long)f * e.nblk * 64;
+    const uint32_t *off = offsets + (long long)f * e.nblk;
+    const uint32_t tbits = (uint32_t)total_bits[f];
+    const uint32_t S = off[b0];
+    const uint32_t E = b1 < e.nblk ? off[b1] : tbits;
+    const bool last = b1 >= e.nblk;
+    const uint32_t wbase = S >> 5;                                   // first staging word
+    const uint32_t W0 = (S + 31u) >> 5;                              // first owned word
+    // padded end of the frame's bit stream (whole bytes)
+    const uint32_t Epad = last ? ((E + 7u) & ~7u) : E;
+    const uint32_t W1 = (Epad + 31u) >> 5;                           // one past the last owned word
+    const int nstage = (int)(W1 - wbase) + 1;
+    for (int i = threadIdx.x; i < nstage && i < kStageWords; i += kPackBlocks) s_stage[i] = 0u;
+    __syncthreads();
+
+    // own blocks, then the few following blocks that reach into the last owned word
+    for (int pass = 0; pass < 2; pass++) {
+        const long long b = pass == 0 ? b0 + threadIdx.x : b1 + threadIdx.x;
+        bool active = pass == 0 ? b < b1 : (threadIdx.x < kLook && b < e.nblk);
+        if (active && pass == 1) active = off[b] < (W1 << 5);
+        if (active) {
+            const int chroma = (int)(b % e.bpm) >= e.hv;
+            const int16_t *c = fc + b * 64;
+            PackSink sink;
+            sink.begin(s_stage, off[b] - (wbase << 5));
+            if (EAGER) walk_block<true>(c, (int)c[0] - prev_dc(fc, b, e), s_dc + 16 * chroma, s_ac + 256 * chroma, sink);
+            else walk_block<false>(c, (int)c[0] - prev_dc(fc, b, e), s_dc + 16 * chroma, s_ac + 256 * chroma, sink);
+            sink.finish();
+        }
+    }
+    if (last && threadIdx.x == 0 && Epad > E) {                      // pad the final byte with 1s
+        const uint32_t pos = E - (wbase << 5), n = Epad - E;
+        atomicOr(s_stage + (pos >> 5), ((1u << n) - 1u) << (32u - (pos & 31u) - n));
+    }
+    __syncthreads();
+    uint32_t *dst = reinterpret_cast<uint32_t *>(unstuffed + (long long)f * ucap);
+    const uint32_t wcap = (uint32_t)(ucap >> 2);
+    for (uint32_t w = W0 + threadIdx.x; w < W1; w += kPackBlocks)
+        if (w < wcap) dst[w] = __byte_perm(s_stage[w - wbase], 0u, 0x0123);     // big-endian bytes
+}
+
+// ---------------------------------------------------------------- K4b: 0xFF stuffing + framing
+constexpr int kStuffChunk = 4096;         // unstuffed bytes per CTA (256 threads x 16)
+
+__device__ __forceinline__ uint32_t ff_mask16(const uint4 &q, int nvalid)
+{
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+        if (i < nvalid && ((w[i >> 2] >> (8 * (i & 3))) & 0xFFu) == 0xFFu) m |= 1u << i;
+    return m;
+}
+
+__global__ void __launch_bounds__(256) k_ff_count(const uint8_t *__restrict__ unstuffed, const int64_t *__restrict__ total_bits,
+                                                  uint32_t *__restrict__ ffpart, long long ucap, int chunks)
+{
+    __shared__ uint32_t s_warp[8];
+    const int f = blockIdx.y, ch = blockIdx.x;
+    const long long nbytes = min((long long)((total_bits[f] + 7) >> 3), ucap);
+    const long long pos = (long long)ch * kStuffChunk + threadIdx.x * 16;
+    uint32_t cnt = 0;
+    if (pos < nbytes) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(unstuffed + (long long)f * ucap + pos);
+        cnt = __popc(ff_mask16(q, (int)min(16LL, nbytes - pos)));
+    }
+    uint32_t tot;
+    cta_excl_scan_256(cnt, s_warp, &tot);
+    if (threadIdx.x == 0) ffpart[(long long)f * chunks + ch] = tot;
+}
+
+// one CTA per frame: exclusive scan of 0xFF counts; final size / capacity verdict
+__global__ void __launch_bounds__(256) k_ff_scan(uint32_t *__restrict__ ffpart, const int64_t *__restrict__ total_bits,
+                                                 int64_t *__restrict__ sizes, long long ucap, long long out_cap, int chunks,
+                                                 int header_bytes)
+{
+    __shared__ uint32_t s_warp[8];
+    uint32_t *p = ffpart + (long long)blockIdx.x * chunks;
+    unsigned long long carry = 0;
+    for (int base = 0; base < chunks; base += 256) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = i < chunks ? p[i] : 0u;
+        uint32_t tot;
+        const uint32_t ex = cta_excl_scan_256(v, s_warp, &tot);
+        if (i < chunks) p[i] = (uint32_t)carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) {
+        const long long nbytes = (total_bits[blockIdx.x] + 7) >> 3;
+        if (nbytes > ucap) sizes[blockIdx.x] = -(header_bytes + 2 * nbytes + 2);      // upper bound of the need
+        else {
+            const long long need = header_bytes + nbytes + (long long)carry + 2;
+            sizes[blockIdx.x] = need <= out_cap ? need : -need;
+        }
+    }
+}
+
+struct HeaderParam { uint8_t bytes[kHeaderBytes + 1]; };
+
+__global__ void __launch_bounds__(256) k_stuff_write(const uint8_t *__restrict__ unstuffed, const int64_t *__restrict__ total_bits,
+                                                     const uint32_t *__restrict__ ffpart, const int64_t *__restrict__ sizes,
+                                                     uint8_t *__restrict__ out, long long ucap, long long out_cap, int chunks,
+                                                     const __grid_constant__ HeaderParam H)
+{
+    __shared__ uint32_t s_warp[8];
+    __shared__ __align__(16) uint8_t s_out[2 * kStuffChunk + 16];
+    const int f = blockIdx.y, ch = blockIdx.x;
+    if (sizes[f] < 0) return;                                       // slot too small: leave it untouched
+    const long long nbytes = (total_bits[f] + 7) >> 3;
+    uint8_t *dst_frame = out + (long long)f * out_cap;
+    if (ch == 0)
+        for (int i = threadIdx.x; i < kHeaderBytes; i += 256) dst_frame[i] = H.bytes[i];
+    const long long pos = (long long)ch * kStuffChunk + threadIdx.x * 16;
+    uint32_t m = 0;
+    int nvalid = 0;
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (pos < nbytes) {
+        nvalid = (int)min(16LL, nbytes - pos);
+        q = *reinterpret_cast<const uint4 *>(unstuffed + (long long)f * ucap + pos);
+        m = ff_mask16(q, nvalid);
+    }
+    uint32_t tot;
+    const uint32_t ex = cta_excl_scan_256(__popc(m), s_warp, &tot);
+    // stuffed bytes of this thread into shared memory at its chunk-relative offset
+    {
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        int o = threadIdx.x * 16 + (int)ex;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            if (i < nvalid) {
+                const uint8_t b = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
+                s_out[o++] = b;
+                if (b == 0xFF) s_out[o++] = 0;
+            }
+        }
+    }
+    __syncthreads();
+    const long long chunk_in = min((long long)kStuffChunk, nbytes - (long long)ch * kStuffChunk);
+    if (chunk_in <= 0) return;
+    const int n_out = (int)chunk_in + (int)tot;
+    uint8_t *dst = dst_frame + kHeaderBytes + (long long)ch * kStuffChunk + ffpart[(long long)f * chunks + ch];
+    // head bytes up to 4-byte alignment, aligned words, tail bytes
+    const int head = min(n_out, (int)((4 - ((uintptr_t)dst & 3)) & 3));
+    if (threadIdx.x < head) dst[threadIdx.x] = s_out[threadIdx.x];
+    const int nwords = (n_out - head) >> 2;
+    uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
+    for (int i = threadIdx.x; i < nwords; i += 256) {
+        const uint8_t *s = s_out + head + 4 * i;
+        dw[i] = (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24);
+    }
+    const int done = head + 4 * nwords;
+    if (threadIdx.x < n_out - done) dst[done + threadIdx.x] = s_out[done + threadIdx.x];
+    // EOI after the last chunk
+    if ((long long)(ch + 1) * kStuffChunk >= nbytes && threadIdx.x == 0) {
+        dst[n_out] = 0xFF;
+        dst[n_out + 1] = 0xD9;
+    }
+}
+
+static LutParam make_lut_param()
+{
+    LutParam L;
+    L.lut = host_huff_lut();
+    return L;
+}
+
+static int scan_chunks(long long nblk) { return (int)((nblk + kScanChunk - 1) / kScanChunk); }
+
+}  // namespace b2j
+
+using namespace b2j;
+
+extern "C" int b2j_block_bits(const int16_t *coefs, const b2j_image_desc *desc, int zrl, int32_t *bits, void *stream)
+{
+    B2J_REQUIRE(coefs && bits, B2J_E_ARG, "b2j_block_bits: null pointer");
+    B2J_REQUIRE(zrl == B2J_ZRL_EAGER || zrl == B2J_ZRL_STANDARD, B2J_E_ARG, "b2j_block_bits: bad zrl policy %d", zrl);
+    B2J_REQUIRE(((uintptr_t)coefs & 15) == 0, B2J_E_ALIGN, "b2j_block_bits: coefs must be 16-byte aligned");
+    Geo g;
+    int rc = make_geo(desc, &g);
+    if (rc) return rc;
+    const EGeo e = egeo_of(g);
+    const long long total = e.nblk * e.n_frames;
+    const LutParam L = make_lut_param();
+    const unsigned grid = (unsigned)((total + 127) / 128);
+    if (zrl == B2J_ZRL_EAGER) k_block_bits<true><<<grid, 128, 0, as_stream(stream)>>>(coefs, bits, e, L);
+    else k_block_bits<false><<<grid, 128, 0, as_stream(stream)>>>(coefs, bits, e, L);
+    B2J_LAUNCH_CHECK("k_block_bits");
+    return B2J_OK;
+}
+
+extern "C" size_t b2j_scan_workspace_bytes(const b2j_image_desc *desc)
+{
+    Geo g;
+    if (make_geo(desc, &g)) return 0;
+    return (size_t)g.n_frames * scan_chunks(g.blocks_per_frame) * sizeof(uint32_t) + 256;
+}
+
+extern "C" int b2j_scan(const int32_t *bits, const b2j_image_desc *desc, uint32_t *offsets, int64_t *total_bits,
+                        void *workspace, void *stream)
+{
+    B2J_REQUIRE(bits && offsets && total_bits && workspace, B2J_E_ARG, "b2j_scan: null pointer");
+    Geo g;
+    int rc = make_geo(desc, &g);
+    if (rc) return rc;
+    const int chunks = scan_chunks(g.blocks_per_frame);
+    uint32_t *partial = reinterpret_cast<uint32_t *>(workspace);
+    cudaStream_t st = as_stream(stream);
+    dim3 grid((unsigned)chunks, (unsigned)g.n_frames);
+    k_chunk_sums<<<grid, 256, 0, st>>>(bits, partial, g.blocks_per_frame, chunks);
+    B2J_LAUNCH_CHECK("k_chunk_sums");
+    k_scan_partials<<<(unsigned)g.n_frames, 256, 0, st>>>(partial, total_bits, chunks);
+    B2J_LAUNCH_CHECK("k_scan_partials");
+    k_scan_apply<<<grid, 256, 0, st>>>(bits, partial, offsets, g.blocks_per_frame, chunks);
+    B2J_LAUNCH_CHECK("k_scan_apply");
+    return B2J_OK;
+}
+
+static long long ucap_of(int64_t out_cap) { return ((long long)out_cap + 15) & ~15LL; }
+static int stuff_chunks(long long ucap) { return (int)((ucap + kStuffChunk - 1) / kStuffChunk); }
+
+extern "C" size_t b2j_bitpack_workspace_bytes(const b2j_image_desc *desc, int64_t out_cap)
+{
+    Geo g;
+    if (make_geo(desc, &g) || out_cap < kHeaderBytes + 2) return 0;
+    const long long ucap = ucap_of(out_cap);
+    return (size_t)g.n_frames * (size_t)ucap + (size_t)g.n_frames * stuff_chunks(ucap) * sizeof(uint32_t) + 512;
+}
+
+extern "C" int b2j_bitpack(const int16_t *coefs, const uint32_t *offsets, const int64_t *total_bits,
+                           const b2j_image_desc *desc, const uint8_t qy_host[64], const uint8_t qc_host[64], int zrl,
+                           void *workspace, uint8_t *out, int64_t out_cap, int64_t *sizes, void *stream)
+{
+    B2J_REQUIRE(coefs && offsets && total_bits && qy_host && qc_host && workspace && out && sizes, B2J_E_ARG,
+                "b2j_bitpack: null pointer");
+    B2J_REQUIRE(zrl == B2J_ZRL_EAGER || zrl == B2J_ZRL_STANDARD, B2J_E_ARG, "b2j_bitpack: bad zrl policy %d", zrl);
+    B2J_REQUIRE(out_cap >= kHeaderBytes + 2, B2J_E_CAPACITY, "b2j_bitpack: out_cap %lld smaller than the header", (long long)out_cap);
+    B2J_REQUIRE(((uintptr_t)coefs & 15) == 0 && ((uintptr_t)workspace & 15) == 0, B2J_E_ALIGN,
+                "b2j_bitpack: coefs and workspace must be 16-byte aligned");
+    Geo g;
+    int rc = make_geo(desc, &g);
+    if (rc) return rc;
+    const EGeo e = egeo_of(g);
+    const long long ucap = ucap_of(out_cap);
+    const int schunks = stuff_chunks(ucap);
+    uint8_t *unstuffed = reinterpret_cast<uint8_t *>(workspace);
+    uint32_t *ffpart = reinterpret_cast<uint32_t *>(unstuffed + (size_t)g.n_frames * (size_t)ucap);
+    HeaderParam H;
+    memset(&H, 0, sizeof H);
+    if (jfif_header(g, qy_host, qc_host, H.bytes) != kHeaderBytes) {
+        set_error("b2j_bitpack: internal header length mismatch");
+        return B2J_E_ARG;
+    }
+    const LutParam L = make_lut_param();
+    cudaStream_t st = as_stream(stream);
+    dim3 pgrid((unsigned)((e.nblk + kPackBlocks - 1) / kPackBlocks), (unsigned)g.n_frames);
+    if (zrl == B2J_ZRL_EAGER) k_bitpack<true><<<pgrid, kPackBlocks, 0, st>>>(coefs, offsets, total_bits, unstuffed, ucap, e, L);
+    else k_bitpack<false><<<pgrid, kPackBlocks, 0, st>>>(coefs, offsets, total_bits, unstuffed, ucap, e, L);
+    B2J_LAUNCH_CHECK("k_bitpack");
+    dim3 sgrid((unsigned)schunks, (unsigned)g.n_frames);
+    k_ff_count<<<sgrid, 256, 0, st>>>(unstuffed, total_bits, ffpart, ucap, schunks);
+    B2J_LAUNCH_CHECK("k_ff_count");
+    k_ff_scan<<<(unsigned)g.n_frames, 256, 0, st>>>(ffpart, total_bits, sizes, ucap, out_cap, schunks, kHeaderBytes);
+    B2J_LAUNCH_CHECK("k_ff_scan");
+    k_stuff_write<<<sgrid, 256, 0, st>>>(unstuffed, total_bits, ffpart, sizes, out, ucap, out_cap, schunks, H);
+    B2J_LAUNCH_CHECK("k_stuff_write");
+    return B2J_OK;
+}

@@ -1,0 +1,523 @@
+// K1: fused colour conversion -> chroma subsampling -> 8x8 DCT (the model's
+// float64 graph) -> quantise -> zig-zag, one pass over the RGB frames.
+// replaces: the loop body test/model/enc_frame.py:203-217 of the reference.
+//
+// Output layout: coefs[frame][mcu][block_in_mcu][64] int16, zig-zag order, MCUs
+// row-major, blocks of an MCU in scan order (luma raster, then Cb, then Cr).
+//
+// Two variants:
+//   simple - one thread per 8x8 block straight from global memory; any geometry;
+//            kept as the cross-check and the un-tiled fallback.
+//   tiled  - persistent CTAs walk tiles of 1024 x (8|16) pixels.  Per tile:
+//            (load)  the RGB rows are brought into shared memory by bulk-async
+//                    copies (cp.async.bulk, one per row, completion on an
+//                    mbarrier) when rows are 16-byte aligned, else by a
+//                    cooperative copy;
+//            (A)     every thread converts 8-pixel patches to Y/Cb/Cr with the
+//                    integer restatement of the model's colour formulas and
+//                    writes 8-bit planes (chroma already subsampled) to smem;
+//            (B)     every thread takes whole 8x8 blocks from the planes, runs
+//                    the model's DCT graph in registers (FP64 pipe), quantises
+//                    and stores 128 B per block.
+//            The next tile's load is issued as soon as (A) has consumed the raw
+//            buffer, so it overlaps (B), which is the long FP64 phase.
+#include "b2j_common.cuh"
+#include "b2j_math.cuh"
+
+namespace b2j {
+
+__device__ __forceinline__ constexpr int zz_of(int i)
+{
+    constexpr uint8_t t[64] = B2J_ZIGZAG_INIT;
+    return t[i];
+}
+
+// Collects the 64 quantised coefficients of one block into 32 packed words in
+// zig-zag order (all indices are compile-time constants -> registers).
+struct BlockPacker {
+    uint32_t w[32];
+    const uint32_t *mul;          // 64 multipliers of this block's table (shared memory)
+    __device__ __forceinline__ void init(const uint32_t *m)
+    {
+        mul = m;
+#pragma unroll
+        for (int i = 0; i < 32; i++) w[i] = 0u;
+    }
+    template <int IDX>
+    __device__ __forceinline__ void put(uint32_t mag, bool neg)
+    {
+        constexpr int z = zz_of(IDX);
+        uint32_t q = quant_mag(mag, mul[IDX]);
+        int r = neg ? -(int)q : (int)q;
+        if (z & 1) w[z >> 1] = (uint32_t)r * 65536u + w[z >> 1];
+        else w[z >> 1] = ((uint32_t)r & 0xFFFFu) | w[z >> 1];
+    }
+    __device__ __forceinline__ void store(int16_t *dst) const
+    {
+        uint4 *o = reinterpret_cast<uint4 *>(dst);
+#pragma unroll
+        for (int i = 0; i < 8; i++) o[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+    }
+};
+
+template <int U, class P>
+__device__ __forceinline__ void emit_col_d(const double (&c)[8], P &p)
+{
+    p.template put<0 * 8 + U>(abs_div8_trunc(c[0]), __double2hiint(c[0]) < 0);
+    p.template put<1 * 8 + U>(abs_div8_trunc(c[1]), __double2hiint(c[1]) < 0);
+    p.template put<2 * 8 + U>(abs_div8_trunc(c[2]), __double2hiint(c[2]) < 0);
+    p.template put<3 * 8 + U>(abs_div8_trunc(c[3]), __double2hiint(c[3]) < 0);
+    p.template put<4 * 8 + U>(abs_div8_trunc(c[4]), __double2hiint(c[4]) < 0);
+    p.template put<5 * 8 + U>(abs_div8_trunc(c[5]), __double2hiint(c[5]) < 0);
+    p.template put<6 * 8 + U>(abs_div8_trunc(c[6]), __double2hiint(c[6]) < 0);
+    p.template put<7 * 8 + U>(abs_div8_trunc(c[7]), __double2hiint(c[7]) < 0);
+}
+
+template <int U, class P>
+__device__ __forceinline__ void emit_col_i(const int (&m)[8], P &p)
+{
+    int r0, r4;
+    double c[8];
+    dct_1d_int(m, r0, r4, c[1], c[2], c[3], c[5], c[6], c[7]);
+    p.template put<0 * 8 + U>((uint32_t)abs(r0) >> 3, r0 < 0);
+    p.template put<4 * 8 + U>((uint32_t)abs(r4) >> 3, r4 < 0);
+    p.template put<1 * 8 + U>(abs_div8_trunc(c[1]), __double2hiint(c[1]) < 0);
+    p.template put<2 * 8 + U>(abs_div8_trunc(c[2]), __double2hiint(c[2]) < 0);
+    p.template put<3 * 8 + U>(abs_div8_trunc(c[3]), __double2hiint(c[3]) < 0);
+    p.template put<5 * 8 + U>(abs_div8_trunc(c[5]), __double2hiint(c[5]) < 0);
+    p.template put<6 * 8 + U>(abs_div8_trunc(c[6]), __double2hiint(c[6]) < 0);
+    p.template put<7 * 8 + U>(abs_div8_trunc(c[7]), __double2hiint(c[7]) < 0);
+}
+
+// 8x8 samples (8 rows of 8 bytes) -> quantised zig-zag block in `p`.
+// Row pass: dct_1d on every row (enc_frame.py:92-100); columns 0 and 4 of the
+// intermediate matrix are integers.  Column pass: enc_frame.py:103-108.
+template <class P>
+__device__ __forceinline__ void dct_quant_block(const uint2 (&px)[8], P &p)
+{
+    int m0[8], m4[8];
+    double m1[8], m2[8], m3[8], m5[8], m6[8], m7[8];
+#pragma unroll
+    for (int x = 0; x < 8; x++) {
+        int s[8];
+        s[0] = (int)(px[x].x & 0xFFu) - 128; s[1] = (int)((px[x].x >> 8) & 0xFFu) - 128;
+        s[2] = (int)((px[x].x >> 16) & 0xFFu) - 128; s[3] = (int)(px[x].x >> 24) - 128;
+        s[4] = (int)(px[x].y & 0xFFu) - 128; s[5] = (int)((px[x].y >> 8) & 0xFFu) - 128;
+        s[6] = (int)((px[x].y >> 16) & 0xFFu) - 128; s[7] = (int)(px[x].y >> 24) - 128;
+        dct_1d_int(s, m0[x], m4[x], m1[x], m2[x], m3[x], m5[x], m6[x], m7[x]);
+    }
+    emit_col_i<0>(m0, p);
+    emit_col_i<4>(m4, p);
+    dct_1d(m1); emit_col_d<1>(m1, p);
+    dct_1d(m2); emit_col_d<2>(m2, p);
+    dct_1d(m3); emit_col_d<3>(m3, p);
+    dct_1d(m5); emit_col_d<5>(m5, p);
+    dct_1d(m6); emit_col_d<6>(m6, p);
+    dct_1d(m7); emit_col_d<7>(m7, p);
+}
+
+struct FusedParams {
+    const uint8_t *rgb;
+    int16_t *coefs;
+    long long row_stride, frame_stride;
+    int width, height;
+    int mcus_x, mcus_y;
+    int n_frames;
+    int aligned;                  // rows may use bulk-async copies
+    QuantMul qm;
+};
+
+// =============================================================== simple variant
+template <int H, int V>
+__global__ void __launch_bounds__(128) k_fused_simple(const __grid_constant__ FusedParams P)
+{
+    constexpr int BPM = H * V + 2;
+    __shared__ uint32_t s_mul[2][64];
+    if (threadIdx.x < 128) s_mul[threadIdx.x >> 6][threadIdx.x & 63] = P.qm.mul[threadIdx.x >> 6][threadIdx.x & 63];
+    __syncthreads();
+    const long long nblk = (long long)P.n_frames * P.mcus_x * P.mcus_y * BPM;
+    const long long gb = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gb >= nblk) return;
+    const int k = (int)(gb % BPM);
+    const long long gm = gb / BPM;
+    const int mx = (int)(gm % P.mcus_x);
+    const int my = (int)((gm / P.mcus_x) % P.mcus_y);
+    const int f = (int)(gm / ((long long)P.mcus_x * P.mcus_y));
+    const uint8_t *img = P.rgb + (long long)f * P.frame_stride;
+    const int comp = k < H * V ? 0 : k - H * V + 1;
+    uint2 px[8];
+    for (int i = 0; i < 8; i++) {
+        uint32_t wds[2] = {0u, 0u};
+        for (int j = 0; j < 8; j++) {
+            uint32_t s;
+            if (comp == 0) {
+                int yy = my * 8 * V + (k / H) * 8 + i, xx = mx * 8 * H + (k % H) * 8 + j;
+                yy = min(yy, P.height - 1); xx = min(xx, P.width - 1);          // edge replication
+                const uint8_t *q = img + (long long)yy * P.row_stride + 3LL * xx;
+                s = rgb2ycbcr_px(q[0], q[1], q[2]) & 0xFFu;
+            } else {
+                int acc_v = 0;
+                for (int dy = 0; dy < V; dy++) {
+                    int acc_h = 0;
+                    for (int dx = 0; dx < H; dx++) {
+                        int yy = min(my * 8 * V + i * V + dy, P.height - 1);
+                        int xx = min(mx * 8 * H + j * H + dx, P.width - 1);
+                        const uint8_t *q = img + (long long)yy * P.row_stride + 3LL * xx;
+                        acc_h += (int)((rgb2ycbcr_px(q[0], q[1], q[2]) >> (8 * comp)) & 0xFFu);
+                    }
+                    acc_v += H == 2 ? acc_h >> 1 : acc_h;                        // crs.py:39-54 pair mean
+                }
+                s = (uint32_t)(V == 2 ? acc_v >> 1 : acc_v);
+            }
+            wds[j >> 2] |= s << (8 * (j & 3));
+        }
+        px[i] = make_uint2(wds[0], wds[1]);
+    }
+    BlockPacker pk;
+    pk.init(s_mul[comp ? 1 : 0]);
+    dct_quant_block(px, pk);
+    pk.store(P.coefs + gb * 64);
+}
+
+// =============================================================== tiled variant
+constexpr int kTileW = 1024;                 // pixels
+constexpr int kRawPitch = kTileW * 3;        // bytes
+constexpr int kThreads = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int H, int V>
+struct TileShape {
+    static constexpr int kRows = 8 * V;                       // pixel rows per tile
+    static constexpr int kCW = kTileW / H;                    // chroma plane width
+    static constexpr int kRawBytes = kRows * kRawPitch;
+    static constexpr int kYBytes = kRows * kTileW;
+    static constexpr int kCBytes = 8 * kCW;
+    static constexpr int kSmem = kRawBytes + kYBytes + 2 * kCBytes + 2 * 64 * 4 + 16;
+};
+
+struct TileCoord {
+    int frame, my, x0;            // MCU row, first pixel column
+    int valid_px, need_px;        // source pixels available / pixels after padding to whole MCUs
+    int valid_rows;
+};
+
+template <int H, int V>
+__device__ __forceinline__ TileCoord tile_coord(const FusedParams &P, long long t, int tiles_x)
+{
+    TileCoord c;
+    c.frame = (int)(t / ((long long)tiles_x * P.mcus_y));
+    int r = (int)(t % ((long long)tiles_x * P.mcus_y));
+    c.my = r / tiles_x;
+    c.x0 = (r % tiles_x) * kTileW;
+    c.valid_px = min(kTileW, P.width - c.x0);
+    c.need_px = min(kTileW, P.mcus_x * 8 * H - c.x0);
+    c.valid_rows = min(8 * V, P.height - c.my * 8 * V);
+    return c;
+}
+
+// colour conversion of one pixel taken from a 24-byte group (8 pixels)
+template <int I>
+__device__ __forceinline__ void px_from_group(const uint32_t (&w)[6], uint32_t &r, uint32_t &g, uint32_t &b)
+{
+    constexpr int j0 = 3 * I, j1 = 3 * I + 1, j2 = 3 * I + 2;
+    r = (w[j0 >> 2] >> (8 * (j0 & 3))) & 0xFFu;
+    g = (w[j1 >> 2] >> (8 * (j1 & 3))) & 0xFFu;
+    b = (w[j2 >> 2] >> (8 * (j2 & 3))) & 0xFFu;
+}
+
+struct Ycc { uint32_t y, cb, cr; };
+
+__device__ __forceinline__ Ycc convert(uint32_t r, uint32_t g, uint32_t b)
+{
+    const uint32_t sy = csc_sum_y(r, g, b), scb = csc_sum_cb(r, g, b), scr = csc_sum_cr(r, g, b);
+    Ycc o;
+    o.y = sy >> 24; o.cb = scb >> 24; o.cr = scr >> 24;
+    if ((sy & B2J_CONST_EXC_MASK) == 0u) o.y = csc_y_fp64(r, g, b);
+    if ((scr & B2J_CONST_EXC_MASK) == 0u) o.cr -= cr_exception(r, g);
+    return o;
+}
+
+template <int H, int V>
+__global__ void __launch_bounds__(kThreads, 2) k_fused_tiled(const __grid_constant__ FusedParams P, long long n_tiles, int tiles_x)
+{
+    using TS = TileShape<H, V>;
+    constexpr int BPM = H * V + 2;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *raw = smem;
+    uint8_t *s_y = raw + TS::kRawBytes;
+    uint8_t *s_cb = s_y + TS::kYBytes;
+    uint8_t *s_cr = s_cb + TS::kCBytes;
+    uint32_t *s_mul = reinterpret_cast<uint32_t *>(s_cr + TS::kCBytes);      // [2][64]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(s_mul + 128);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    s_mul[tid] = P.qm.mul[tid >> 6][tid & 63];
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue_load = [&](const TileCoord &c) -> bool {
+        // bulk-async path needs 16-byte aligned rows and a 16-byte multiple of bytes per row
+        const bool bulk = P.aligned && ((c.valid_px * 3) & 15) == 0;
+        if (bulk && tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar, (uint32_t)(c.valid_rows * c.valid_px * 3));
+            const uint8_t *src = P.rgb + (long long)c.frame * P.frame_stride +
+                                 (long long)(c.my * 8 * V) * P.row_stride + 3LL * c.x0;
+            for (int r = 0; r < c.valid_rows; r++)
+                bulk_g2s(raw + r * kRawPitch, src + (long long)r * P.row_stride, (uint32_t)(c.valid_px * 3), bar);
+        }
+        return bulk;
+    };
+
+    long long t = blockIdx.x;
+    if (t >= n_tiles) return;
+    TileCoord cur = tile_coord<H, V>(P, t, tiles_x);
+    bool cur_bulk = issue_load(cur);
+    uint32_t phase = 0;
+
+    for (; t < n_tiles; t += gridDim.x) {
+        // ---------------- wait for / perform the load of the current tile
+        if (cur_bulk) {
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+        } else {
+            const uint8_t *src = P.rgb + (long long)cur.frame * P.frame_stride +
+                                 (long long)(cur.my * 8 * V) * P.row_stride + 3LL * cur.x0;
+            const int nbytes = cur.valid_px * 3;
+            for (int r = 0; r < cur.valid_rows; r++)
+                for (int i = tid; i < nbytes; i += kThreads) raw[r * kRawPitch + i] = src[(long long)r * P.row_stride + i];
+            __syncthreads();
+        }
+        // ---------------- edge replication up to whole MCUs (uniform branch, edge tiles only)
+        if (cur.valid_px < cur.need_px || cur.valid_rows < TS::kRows) {
+            const int pad = (cur.need_px - cur.valid_px) * 3;
+            for (int i = tid; i < cur.valid_rows * pad; i += kThreads) {
+                const int r = i / pad, j = i % pad;
+                raw[r * kRawPitch + cur.valid_px * 3 + j] = raw[r * kRawPitch + (cur.valid_px - 1) * 3 + j % 3];
+            }
+            __syncthreads();
+            const int nb = cur.need_px * 3;
+            for (int r = cur.valid_rows; r < TS::kRows; r++)
+                for (int i = tid; i < nb; i += kThreads) raw[r * kRawPitch + i] = raw[(cur.valid_rows - 1) * kRawPitch + i];
+            __syncthreads();
+        }
+
+        // ---------------- phase A: colour conversion + subsampling into 8-bit planes
+        // thread `tid` owns the 8-pixel column group `tid` of every row (pair)
+        if (tid * 8 < cur.need_px) {
+#pragma unroll 1
+            for (int ry = 0; ry < 8; ry++) {
+                uint32_t wa[6], wb[6];
+                {
+                    const uint2 *p = reinterpret_cast<const uint2 *>(raw + (ry * V) * kRawPitch + tid * 24);
+                    uint2 a = p[0], b = p[1], c = p[2];
+                    wa[0] = a.x; wa[1] = a.y; wa[2] = b.x; wa[3] = b.y; wa[4] = c.x; wa[5] = c.y;
+                }
+                if (V == 2) {
+                    const uint2 *p = reinterpret_cast<const uint2 *>(raw + (ry * 2 + 1) * kRawPitch + tid * 24);
+                    uint2 a = p[0], b = p[1], c = p[2];
+                    wb[0] = a.x; wb[1] = a.y; wb[2] = b.x; wb[3] = b.y; wb[4] = c.x; wb[5] = c.y;
+                }
+                Ycc A[8], B[8];
+                {
+                    uint32_t r, g, b;
+                    px_from_group<0>(wa, r, g, b); A[0] = convert(r, g, b);
+                    px_from_group<1>(wa, r, g, b); A[1] = convert(r, g, b);
+                    px_from_group<2>(wa, r, g, b); A[2] = convert(r, g, b);
+                    px_from_group<3>(wa, r, g, b); A[3] = convert(r, g, b);
+                    px_from_group<4>(wa, r, g, b); A[4] = convert(r, g, b);
+                    px_from_group<5>(wa, r, g, b); A[5] = convert(r, g, b);
+                    px_from_group<6>(wa, r, g, b); A[6] = convert(r, g, b);
+                    px_from_group<7>(wa, r, g, b); A[7] = convert(r, g, b);
+                    if (V == 2) {
+                        px_from_group<0>(wb, r, g, b); B[0] = convert(r, g, b);
+                        px_from_group<1>(wb, r, g, b); B[1] = convert(r, g, b);
+                        px_from_group<2>(wb, r, g, b); B[2] = convert(r, g, b);
+                        px_from_group<3>(wb, r, g, b); B[3] = convert(r, g, b);
+                        px_from_group<4>(wb, r, g, b); B[4] = convert(r, g, b);
+                        px_from_group<5>(wb, r, g, b); B[5] = convert(r, g, b);
+                        px_from_group<6>(wb, r, g, b); B[6] = convert(r, g, b);
+                        px_from_group<7>(wb, r, g, b); B[7] = convert(r, g, b);
+                    }
+                }
+                // luma
+                {
+                    uint2 o;
+                    o.x = A[0].y | (A[1].y << 8) | (A[2].y << 16) | (A[3].y << 24);
+                    o.y = A[4].y | (A[5].y << 8) | (A[6].y << 16) | (A[7].y << 24);
+                    *reinterpret_cast<uint2 *>(s_y + (ry * V) * kTileW + tid * 8) = o;
+                    if (V == 2) {
+                        o.x = B[0].y | (B[1].y << 8) | (B[2].y << 16) | (B[3].y << 24);
+                        o.y = B[4].y | (B[5].y << 8) | (B[6].y << 16) | (B[7].y << 24);
+                        *reinterpret_cast<uint2 *>(s_y + (ry * 2 + 1) * kTileW + tid * 8) = o;
+                    }
+                }
+                // chroma: pair mean (c0 + c1) >> 1 horizontally (crs.py:39-54), then vertically
+                if (H == 1) {
+                    uint2 o;
+                    o.x = A[0].cb | (A[1].cb << 8) | (A[2].cb << 16) | (A[3].cb << 24);
+                    o.y = A[4].cb | (A[5].cb << 8) | (A[6].cb << 16) | (A[7].cb << 24);
+                    *reinterpret_cast<uint2 *>(s_cb + ry * TS::kCW + tid * 8) = o;
+                    o.x = A[0].cr | (A[1].cr << 8) | (A[2].cr << 16) | (A[3].cr << 24);
+                    o.y = A[4].cr | (A[5].cr << 8) | (A[6].cr << 16) | (A[7].cr << 24);
+                    *reinterpret_cast<uint2 *>(s_cr + ry * TS::kCW + tid * 8) = o;
+                } else {
+                    uint32_t ocb = 0u, ocr = 0u;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        uint32_t cb = (A[2 * j].cb + A[2 * j + 1].cb) >> 1, cr = (A[2 * j].cr + A[2 * j + 1].cr) >> 1;
+                        if (V == 2) {
+                            cb = (cb + ((B[2 * j].cb + B[2 * j + 1].cb) >> 1)) >> 1;
+                            cr = (cr + ((B[2 * j].cr + B[2 * j + 1].cr) >> 1)) >> 1;
+                        }
+                        ocb |= cb << (8 * j);
+                        ocr |= cr << (8 * j);
+                    }
+                    *reinterpret_cast<uint32_t *>(s_cb + ry * TS::kCW + tid * 4) = ocb;
+                    *reinterpret_cast<uint32_t *>(s_cr + ry * TS::kCW + tid * 4) = ocr;
+                }
+            }
+        }
+        __syncthreads();        // planes complete; raw buffer is free again
+
+        // ---------------- prefetch the next tile while phase B runs
+        const long long tn = t + gridDim.x;
+        TileCoord nxt = cur;
+        bool nxt_bulk = false;
+        if (tn < n_tiles) {
+            nxt = tile_coord<H, V>(P, tn, tiles_x);
+            nxt_bulk = issue_load(nxt);
+        }
+
+        // ---------------- phase B: one 8x8 block per thread, warp-uniform component class
+        {
+            const int nbx = cur.need_px >> 3;                  // luma blocks per block row
+            const int ncx = nbx / H;                           // chroma blocks per component
+            const long long mcu_base = ((long long)cur.frame * P.mcus_y + cur.my) * P.mcus_x + cur.x0 / (8 * H);
+            constexpr int kYTasks = V * (kTileW / 8 / 32);     // 32 consecutive blocks of one block row each
+            constexpr int kCTasksPer = kTileW / H / 8 / 32;    // per chroma component
+            constexpr int kTasks = kYTasks + 2 * kCTasksPer;
+#pragma unroll 1
+            for (int task = warp; task < kTasks; task += kThreads / 32) {
+                const uint8_t *plane;
+                int pitch, bx, row0, k;
+                const uint32_t *mul;
+                if (task < kYTasks) {
+                    const int by = task / (kTileW / 8 / 32);
+                    bx = (task % (kTileW / 8 / 32)) * 32 + lane;
+                    if (bx >= nbx) continue;
+                    plane = s_y; pitch = kTileW; row0 = by * 8;
+                    k = by * H + (bx % H);
+                    mul = s_mul;
+                    const long long mcu = mcu_base + bx / H;
+                    uint2 px[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) px[i] = *reinterpret_cast<const uint2 *>(plane + (row0 + i) * pitch + bx * 8);
+                    BlockPacker pk;
+                    pk.init(mul);
+                    dct_quant_block(px, pk);
+                    pk.store(P.coefs + (mcu * BPM + k) * 64);
+                } else {
+                    const int ct = task - kYTasks;
+                    const int comp = ct / kCTasksPer;           // 0 = Cb, 1 = Cr
+                    bx = (ct % kCTasksPer) * 32 + lane;
+                    if (bx >= ncx) continue;
+                    plane = comp ? s_cr : s_cb; pitch = TS::kCW;
+                    k = H * V + comp;
+                    mul = s_mul + 64;
+                    const long long mcu = mcu_base + bx;
+                    uint2 px[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) px[i] = *reinterpret_cast<const uint2 *>(plane + i * pitch + bx * 8);
+                    BlockPacker pk;
+                    pk.init(mul);
+                    dct_quant_block(px, pk);
+                    pk.store(P.coefs + (mcu * BPM + k) * 64);
+                }
+            }
+        }
+        __syncthreads();        // planes may be overwritten by the next phase A
+        cur = nxt;
+        cur_bulk = nxt_bulk;
+    }
+}
+
+template <int H, int V>
+static int launch_fused(const FusedParams &P, const Geo &g, int variant, cudaStream_t st)
+{
+    if (variant == B2J_FUSED_SIMPLE) {
+        const long long nblk = (long long)g.n_frames * g.blocks_per_frame;
+        k_fused_simple<H, V><<<(unsigned)((nblk + 127) / 128), 128, 0, st>>>(P);
+        B2J_LAUNCH_CHECK("k_fused_simple");
+        return B2J_OK;
+    }
+    using TS = TileShape<H, V>;
+    const int tiles_x = (g.mcus_x * 8 * H + kTileW - 1) / kTileW;
+    const long long n_tiles = (long long)tiles_x * g.mcus_y * g.n_frames;
+    int dev = 0, sms = 148;
+    B2J_CUDA(cudaGetDevice(&dev));
+    B2J_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    B2J_CUDA(cudaFuncSetAttribute(k_fused_tiled<H, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS::kSmem));
+    const long long grid = n_tiles < 2LL * sms ? n_tiles : 2LL * sms;      // 2 resident CTAs per SM
+    k_fused_tiled<H, V><<<(unsigned)grid, kThreads, TS::kSmem, st>>>(P, n_tiles, tiles_x);
+    B2J_LAUNCH_CHECK("k_fused_tiled");
+    return B2J_OK;
+}
+
+}  // namespace b2j
+
+using namespace b2j;
+
+extern "C" int b2j_fused_block(const uint8_t *rgb, const b2j_image_desc *desc, const uint8_t qy_host[64],
+                               const uint8_t qc_host[64], int16_t *coefs, int variant, void *stream)
+{
+    B2J_REQUIRE(rgb && coefs && qy_host && qc_host, B2J_E_ARG, "b2j_fused_block: null pointer");
+    B2J_REQUIRE(variant >= B2J_FUSED_AUTO && variant <= B2J_FUSED_TILED, B2J_E_ARG, "b2j_fused_block: bad variant %d", variant);
+    B2J_REQUIRE(((uintptr_t)coefs & 15) == 0, B2J_E_ALIGN, "b2j_fused_block: coefs must be 16-byte aligned");
+    Geo g;
+    int rc = make_geo(desc, &g);
+    if (rc) return rc;
+    for (int i = 0; i < 64; i++)
+        B2J_REQUIRE(qy_host[i] >= 1 && qc_host[i] >= 1, B2J_E_ARG, "b2j_fused_block: zero quantiser at %d", i);
+    FusedParams P;
+    P.rgb = rgb; P.coefs = coefs;
+    P.row_stride = g.row_stride; P.frame_stride = g.frame_stride;
+    P.width = g.width; P.height = g.height; P.mcus_x = g.mcus_x; P.mcus_y = g.mcus_y; P.n_frames = g.n_frames;
+    P.aligned = (((uintptr_t)rgb & 15) == 0 && (g.row_stride & 15) == 0 && (g.frame_stride & 15) == 0) ? 1 : 0;
+    make_quant_mul(qy_host, qc_host, &P.qm);
+    cudaStream_t st = as_stream(stream);
+    if (variant == B2J_FUSED_AUTO) variant = B2J_FUSED_TILED;
+    if (g.h == 1) return launch_fused<1, 1>(P, g, variant, st);
+    if (g.v == 1) return launch_fused<2, 1>(P, g, variant, st);
+    return launch_fused<2, 2>(P, g, variant, st);
+}

@@ -1,0 +1,200 @@
+"""The fused encode path K1..K4 on the GPU against the oracle: coefficients, bit counts,
+offsets and the final JFIF bytes must be identical.  All calls go through the C ABI."""
+import ctypes
+import io
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import jpeg_ext as J
+from oracle import model_np as M
+
+pytestmark = pytest.mark.gpu
+
+SUBS = ["444", "422", "420"]
+
+
+def synth(lj):
+    import importlib
+    return importlib.import_module("litejpeg_b200.synth")
+
+
+def test_lena_config1_coefficients_are_the_models(lj, golden):
+    """BASELINE config 1: lena 512x512, 4:4:4, model tables: every block == enc_frame.py output."""
+    rgb = torch.from_numpy(golden.lena["rgb"]).cuda()
+    enc = lj.JpegEncoder("444", tables=(M.y_quant_table.tolist(), M.cbcr_quant_table.tolist()))
+    zz = golden.lena["zigzag"]
+    for variant in ("simple", "tiled"):
+        coefs = enc.coefficients(rgb, variant=variant).cpu().numpy()[0].reshape(4096, 3, 64)
+        for c in range(3):
+            assert np.array_equal(coefs[:, c], zz[c]), (variant, c)
+    enc85 = lj.JpegEncoder("444", quality=85)                        # q85 == the model's tables
+    assert np.array_equal(enc85.coefficients(rgb).cpu().numpy(), enc.coefficients(rgb).cpu().numpy())
+
+
+@pytest.mark.parametrize("sub", SUBS)
+@pytest.mark.parametrize("shape", [(8, 8), (16, 16), (37, 53), (96, 120), (64, 1040), (40, 2064), (17, 1025)])
+def test_coefficients_any_geometry(lj, oracle_c, sub, shape):
+    """Edge replication, ragged sides, several tiles per row, unaligned row strides."""
+    h, w = shape
+    g = torch.Generator().manual_seed(h * 10007 + w)
+    rgb = torch.randint(0, 256, (2, h, w, 3), generator=g, dtype=torch.uint8)
+    qy, qc = J.quant_tables(75)
+    enc = lj.JpegEncoder(sub, quality=75)
+    exp = np.stack([oracle_c.coefficients(rgb[i].numpy(), sub, qy, qc).reshape(-1, 64) for i in range(2)])
+    for variant in ("simple", "tiled"):
+        got = enc.coefficients(rgb.cuda(), variant=variant).cpu().numpy()
+        assert np.array_equal(got, exp), variant
+
+
+@pytest.mark.parametrize("sub", SUBS)
+@pytest.mark.parametrize("zrl", ["eager", "standard"])
+def test_stagewise_entropy_path(lj, oracle_c, golden, sub, zrl):
+    """K2 bits, K3 offsets, K4 bytes, each against the oracle, on a lena crop (2 frames)."""
+    crop = golden.lena["rgb"][64:64 + 200, 32:32 + 328]
+    rgb = torch.from_numpy(np.stack([crop, crop[::-1].copy()])).cuda()
+    enc = lj.JpegEncoder(sub, quality=85, zrl=zrl)
+    desc = enc.desc_for(rgb)
+    coefs = enc.coefficients(rgb)
+    bits = lj.Huffman(zrl).process(coefs, desc)
+    offsets, total = lj.BitPack(zrl).scan(bits, desc)
+    out, sizes = lj.BitPack(zrl).process(coefs, bits, desc, enc.qy, enc.qc)
+    zi = 0 if zrl == "eager" else 1
+    for f in range(2):
+        frame = rgb[f].cpu().numpy()
+        c = coefs[f].cpu().numpy()
+        ebits = oracle_c.block_bits(c, 200, 328, sub, zi)
+        assert np.array_equal(bits[f].cpu().numpy(), ebits)
+        eoff = np.cumsum(ebits) - ebits
+        assert np.array_equal(offsets[f].cpu().numpy().astype(np.uint32), eoff.astype(np.uint32))
+        assert int(total[f]) == int(ebits.sum())
+        ref = oracle_c.encode_jpeg(frame, sub, 85, zi)
+        n = int(sizes[f])
+        assert n == len(ref)
+        assert out[f, :n].cpu().numpy().tobytes() == ref
+
+
+@pytest.mark.parametrize("sub", SUBS)
+@pytest.mark.parametrize("kind", ["photo", "noise", "grey"])
+def test_full_encode_bytes_equal_oracle(lj, oracle_c, sub, kind):
+    s = synth(lj)
+    frames = torch.stack([s.frame(120, 200, 9, i, kind) for i in range(3)])
+    for q, zrl in ((75, "eager"), (90, "standard"), (100, "eager"), (10, "eager")):
+        enc = lj.JpegEncoder(sub, quality=q, zrl=zrl, out_cap=120 * 200 * 8)
+        files = enc.encode(frames.cuda())
+        for i, f in enumerate(files):
+            assert f == oracle_c.encode_jpeg(frames[i].numpy(), sub, q, 0 if zrl == "eager" else 1), (q, zrl, i)
+
+
+def test_lena_files_decode(lj, oracle_c, golden):
+    """The emitted files open in PIL / OpenCV and the oracle decoder recovers the model's coefficients."""
+    from PIL import Image
+    rgb = golden.lena["rgb"]
+    for sub in SUBS:
+        enc = lj.JpegEncoder(sub, quality=85)
+        jpg = enc.encode(torch.from_numpy(rgb).cuda())[0]
+        assert jpg[:2] == b"\xFF\xD8" and jpg[-2:] == b"\xFF\xD9"
+        pil = np.array(Image.open(io.BytesIO(jpg)).convert("RGB")).astype(np.float64)
+        psnr = 10 * np.log10(255 ** 2 / np.mean((pil - rgb) ** 2))
+        assert psnr > 32, (sub, psnr)
+        rc, dec = oracle_c.decode_coefficients(jpg, 512, 512, sub)
+        assert rc == 0
+        assert np.array_equal(dec.reshape(-1, 64), enc.coefficients(torch.from_numpy(rgb).cuda()).cpu().numpy()[0])
+        if sub == "444":
+            zz = golden.lena["zigzag"]
+            for c in range(3):
+                assert np.array_equal(dec[:, c], zz[c])
+        try:
+            import cv2
+            assert cv2.imdecode(np.frombuffer(jpg, np.uint8), cv2.IMREAD_COLOR).shape == (512, 512, 3)
+        except ImportError:
+            pass
+
+
+@pytest.mark.parametrize("cfg", [(1080, 1920, "420", 75, 2), (2160, 3840, "444", 90, 4), (2160, 3840, "420", 90, 4),
+                                 (4320, 7680, "420", 75, 5)])
+def test_full_size_frames_bytes_equal_oracle(lj, oracle_c, cfg):
+    """BASELINE configs 2-5 at full frame size (one frame each): bytes identical to the C oracle,
+    and the oracle decoder recovers the kernel's coefficients from the file."""
+    h, w, sub, q, idx = cfg
+    s = synth(lj)
+    frame = s.frame(h, w, idx, 0, "photo")
+    enc = lj.JpegEncoder(sub, quality=q)
+    dev = frame.cuda()[None]
+    jpg = enc.encode(dev)[0]
+    ref = oracle_c.encode_jpeg(frame.numpy(), sub, q, 0)
+    assert len(jpg) == len(ref)
+    assert jpg == ref
+    rc, dec = oracle_c.decode_coefficients(jpg, h, w, sub)
+    assert rc == 0 and np.array_equal(dec.reshape(-1, 64), enc.coefficients(dev).cpu().numpy()[0])
+
+
+def test_stress_8k_noise_and_grey(lj, oracle_c):
+    """SURVEY 8d stress distributions on one 8K frame: worst-case scan / bit packer, and EOB-only."""
+    s = synth(lj)
+    for kind in ("noise", "grey"):
+        frame = s.frame(4320, 7680, 5, 0, kind)
+        enc = lj.JpegEncoder("420", quality=75, out_cap=4320 * 7680 * 3)
+        jpg = enc.encode(frame.cuda()[None])[0]
+        assert jpg == oracle_c.encode_jpeg(frame.numpy(), "420", 75, 0), kind
+
+
+def test_batch_properties(lj, oracle_c):
+    """Size-independent properties on a batch: frames are independent (same frame -> same bytes
+    wherever it sits in the batch), and a checksum of checksums equals the per-frame oracle."""
+    import hashlib
+    s = synth(lj)
+    uniq = torch.stack([s.frame(1080, 1920, 3, i) for i in range(4)])
+    order = [0, 1, 2, 3, 3, 1, 0, 2, 2, 2, 0, 1]
+    batch = uniq[order].cuda()
+    enc = lj.JpegEncoder("420", quality=75)
+    files = enc.encode(batch)
+    ref = [oracle_c.encode_jpeg(uniq[i].numpy(), "420", 75, 0) for i in range(4)]
+    for pos, i in enumerate(order):
+        assert files[pos] == ref[i], pos
+    top = hashlib.sha256(b"".join(hashlib.sha256(f).digest() for f in files)).hexdigest()
+    assert top == hashlib.sha256(b"".join(hashlib.sha256(ref[i]).digest() for i in order)).hexdigest()
+
+
+def test_capacity_error_is_reported(lj):
+    s = synth(lj)
+    frame = s.frame(64, 64, 1, 0, "noise").cuda()[None]
+    enc = lj.JpegEncoder("444", quality=95, out_cap=1024)
+    out, sizes = enc.encode_device(frame)
+    assert int(sizes[0]) < 0 and -int(sizes[0]) > 1024
+    with pytest.raises(lj.B2JError):
+        enc.encode(frame)
+    big = lj.JpegEncoder("444", quality=95, out_cap=-int(sizes[0]) + 64)
+    assert len(big.encode(frame)[0]) <= -int(sizes[0])
+
+
+def test_host_buffer_encoder_matches_device_path(lj, oracle_c):
+    """The end-to-end entry point (host buffers, chunked copies) gives the same files."""
+    s = synth(lj)
+    frames = torch.stack([s.frame(360, 640, 6, i) for i in range(7)])
+    enc = lj.JpegEncoder("420", quality=75)
+    ref = [oracle_c.encode_jpeg(frames[i].numpy(), "420", 75, 0) for i in range(7)]
+    for pinned in (False, True):
+        src = frames.pin_memory() if pinned else frames
+        out, sizes = enc.encode_host(src, frames_per_chunk=3)
+        for i in range(7):
+            assert out[i, :int(sizes[i])].numpy().tobytes() == ref[i], (pinned, i)
+    enc.close()
+
+
+def test_strided_input_through_the_c_abi(lj, oracle_c):
+    """row_stride / frame_stride of b2j_image_desc: a crop of a larger device buffer, no copy."""
+    s = synth(lj)
+    big = s.frame(128, 256, 4, 0).cuda()
+    crop_h, crop_w, y0, x0 = 72, 104, 16, 32
+    desc = lj.make_desc(crop_h, crop_w, "420", 1, row_stride=256 * 3, frame_stride=256 * 3 * 128)
+    g = lj.geometry(desc)
+    qy, qc = lj.quant_tables(75)
+    coefs = torch.empty((1, g.blocks_per_frame, 64), dtype=torch.int16, device="cuda")
+    base = big.data_ptr() + (y0 * 256 + x0) * 3
+    for variant in (1, 2):
+        lj._lib.check(lj.lib().b2j_fused_block(base, ctypes.byref(desc), lj._lib.table_arg(qy), lj._lib.table_arg(qc),
+                                               coefs.data_ptr(), variant, torch.cuda.current_stream().cuda_stream))
+        exp = oracle_c.coefficients(big[y0:y0 + crop_h, x0:x0 + crop_w].cpu().numpy(), "420", *J.quant_tables(75))
+        assert np.array_equal(coefs.cpu().numpy()[0], exp.reshape(-1, 64)), variant

@@ -1,0 +1,79 @@
+"""The plain-C oracle (oracle/c/b2j_oracle.c) against the NumPy oracle and the golden
+fixtures.  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import jpeg_ext as J
+from oracle import model_np as M
+
+
+def test_c_stage_functions(oracle_c, golden):
+    s = golden.stages
+    lib = oracle_c.lib
+    p = oracle_c._p
+    rgb = np.ascontiguousarray(s["rgb"].astype(np.uint8))
+    n = rgb.shape[0]
+    y, cb, cr = (np.zeros(n, np.uint8) for _ in range(3))
+    lib.b2jo_rgb2ycbcr(p(rgb), n, p(y), p(cb), p(cr))
+    assert np.array_equal(np.stack([y, cb, cr], 1), s["ycbcr"])
+    din = np.ascontiguousarray(s["dct_in"].astype(np.int32))
+    dout = np.zeros_like(din)
+    lib.b2jo_dct(p(din), din.shape[0], p(dout))
+    assert np.array_equal(dout, s["dct_out"])
+    q = np.zeros_like(dout)
+    tab = np.ascontiguousarray(s["y_quant_table"].astype(np.int32))
+    lib.b2jo_quantize(p(dout), dout.shape[0], p(tab), p(q))
+    assert np.array_equal(q, s["quant_y"])
+    z = np.zeros_like(q)
+    lib.b2jo_zigzag(p(q), q.shape[0], p(z))
+    assert np.array_equal(z, s["zigzag_out"])
+
+
+def test_c_lena_coefficients_are_the_model(oracle_c, golden):
+    rgb = golden.lena["rgb"]
+    coefs = oracle_c.coefficients(rgb, 444, M.y_quant_table, M.cbcr_quant_table)
+    zz = golden.lena["zigzag"]
+    for c in range(3):
+        assert np.array_equal(coefs[:, c], zz[c])
+
+
+@pytest.mark.parametrize("sub", ["444", "422", "420"])
+@pytest.mark.parametrize("zrl", [0, 1])
+@pytest.mark.parametrize("shape", [(8, 8), (16, 16), (37, 53), (96, 120)])
+def test_c_bitstream_equals_numpy(oracle_c, golden, sub, zrl, shape):
+    h, w = shape
+    rng = np.random.default_rng(h * 1000 + w)
+    if h <= 37:
+        rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    else:
+        rgb = np.ascontiguousarray(golden.lena["rgb"][100:100 + h, 60:60 + w])
+    ref = J.encode_jpeg(rgb, sub, 75, "eager" if zrl == 0 else "standard")
+    got = oracle_c.encode_jpeg(rgb, sub, 75, zrl)
+    assert got == ref
+    rc, coefs = oracle_c.decode_coefficients(got, h, w, sub)
+    assert rc == 0
+    exp, geo = J.encode_coefficients(rgb, sub, quality=75)
+    assert np.array_equal(coefs, exp)
+    bits = oracle_c.block_bits(exp, h, w, sub, zrl)
+    assert np.array_equal(bits.reshape(exp.shape[:2]), J.block_bit_lengths(exp, geo, "eager" if zrl == 0 else "standard"))
+
+
+def test_c_quality_tables(oracle_c):
+    for q in (1, 10, 49, 50, 75, 85, 90, 100):
+        qy, qc = oracle_c.quant_tables(q)
+        ey, ec = J.quant_tables(q)
+        assert np.array_equal(qy, ey) and np.array_equal(qc, ec)
+
+
+def test_c_special_content(oracle_c):
+    # constant grey (EOB-only blocks) and saturated noise, all modes
+    for kind in ("grey", "noise", "extremes"):
+        if kind == "grey":
+            rgb = np.full((32, 48, 3), 128, np.uint8)
+        elif kind == "noise":
+            rgb = np.random.default_rng(5).integers(0, 256, (32, 48, 3), dtype=np.uint8)
+        else:
+            rgb = (np.indices((32, 48)).sum(0) % 2 * 255).astype(np.uint8)[..., None].repeat(3, 2)
+        for sub in ("444", "422", "420"):
+            for q in (50, 100):
+                assert oracle_c.encode_jpeg(rgb, sub, q, 0) == J.encode_jpeg(rgb, sub, q, "eager")
