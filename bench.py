@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 JPEG encode path (driver contract: one JSON line on stdout).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on host cores
+
+Workload (BASELINE.json configs[2], the configuration the Mpixel/s metric is quoted on): per GPU a
+batch of 256 synthetic 1920x1080 RGB frames, 4:2:0, quality 75 -> 256 JFIF files.  One "step" is one
+pass of the whole hot path (K1 fused block kernel, K2 block bits, K3 scan, K4 bit pack + stuffing)
+over that batch.  Frames are independent, so ranks shard by frames with no data-path collective
+(weak scaling: every rank encodes its own 256-frame batch).
+
+value : whole-job Mpixel/s (source pixels) with the batch already resident in HBM, CUDA-event timed,
+        max over ranks.  The 1.59 GB input is far larger than the 126 MB L2, so every step streams
+        from HBM (config.l2 = "input > L2").
+e2e   : the same metric through the host-buffer entry point of the C ABI
+        (b2j_encoder_encode_host): pinned host RGB in, JFIF bytes in pinned host memory out, H2D and
+        D2H copies inside the timed region.
+roofline : K1 (the dominant kernel), algorithmic bytes 6 B per padded pixel (3 B RGB read + 1.5
+        int16 coefficients written) / its mean duration measured with CUDA events inside the timed
+        steps, against MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline : the plain-C oracle port (oracle/c/b2j_oracle.c, OpenMP) on this box's host cores on
+        a bounded sample of the same batch.  The reference's own Python model cannot travel to the
+        GPU box (and runs at 0.069 Mpixel/s); see DESIGN.md.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, W, SUB, QUALITY, ZRL = 1080, 1920, "420", 75, "eager"
+FRAMES_PER_GPU = 256
+UNIQUE_FRAMES = 32
+CONFIG_IDX = 2
+METRIC = "Mpixel/s full JPEG encode (RGB -> JFIF bytes)"
+UNIT = "Mpixel/s"
+CPU_SAMPLE_FRAMES = 64
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU (default: the named workload)")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(n_gpus, frames):
+    return {"workload": "batch of %d synthetic 1920x1080 RGB frames per GPU, 4:2:0, quality 75 (BASELINE configs[2])" % frames,
+            "frames_per_gpu": frames, "global_frames": frames * n_gpus, "height": H, "width": W, "subsampling": SUB,
+            "quality": QUALITY, "zrl_policy": ZRL, "unique_frames": min(UNIQUE_FRAMES, frames),
+            "parallelism": "frames sharded across %d GPU(s), no data-path collective" % n_gpus,
+            "l2": "input (%.2f GB per GPU) > L2 (126 MB): every step streams from HBM" % (frames * H * W * 3 / 1e9)}
+
+
+# ---------------------------------------------------------------------------------- CPU arm
+class OraclePort:
+    def __init__(self):
+        path = os.path.join(ROOT, "oracle", "_build", "libb2j_oracle.so")
+        if not os.path.exists(path):
+            res = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], capture_output=True, text=True)
+            if res.returncode:
+                raise RuntimeError("cannot build the C oracle: " + res.stderr)
+        self.lib = ctypes.CDLL(path)
+        self.threads = int(self.lib.b2jo_num_threads())
+
+    def encode_batch(self, frames_np, out_np, sizes_np, cap):
+        n = frames_np.shape[0]
+        rc = self.lib.b2jo_encode_batch(frames_np.ctypes.data_as(ctypes.c_void_p), n, H, W, int(SUB), QUALITY,
+                                        0 if ZRL == "eager" else 1, out_np.ctypes.data_as(ctypes.c_void_p),
+                                        ctypes.c_int64(cap), sizes_np.ctypes.data_as(ctypes.c_void_p), 0)
+        assert rc == 0
+
+
+def cpu_baseline(frames_torch, steps=1):
+    """Times the oracle port on a bounded sample (first CPU_SAMPLE_FRAMES frames), all host threads."""
+    import numpy as np
+    port = OraclePort()
+    n = min(CPU_SAMPLE_FRAMES, frames_torch.shape[0])
+    sample = frames_torch[:n].numpy()
+    cap = H * W * 3 // 2 + 4096
+    out = np.zeros((n, cap), np.uint8)
+    sizes = np.zeros(n, np.int64)
+    port.encode_batch(sample[:min(8, n)], out, sizes, cap)          # warm-up (page faults, table init)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        port.encode_batch(sample, out, sizes, cap)
+        times.append(time.perf_counter() - t0)
+    assert (sizes > 0).all()
+    dt = sum(times) / len(times)
+    return {"value": n * H * W / dt / 1e6, "unit": UNIT, "cores": port.threads, "kind": "port",
+            "sample": "%d of the %d frames (%.1f Mpixel) per step, OpenMP over frames, %d threads; %.2f s per step"
+                      % (n, frames_torch.shape[0], n * H * W / 1e6, port.threads, dt)}, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import importlib
+    import litejpeg_b200  # noqa: F401  (only for the synthetic frame generator; no GPU work on this arm)
+    synth = importlib.import_module("litejpeg_b200.synth")
+    n = min(CPU_SAMPLE_FRAMES, args.frames)
+    frames = synth.batch(n, H, W, CONFIG_IDX, "photo", unique=min(UNIQUE_FRAMES, n))
+    for _ in range(max(0, args.warmup - 1)):
+        cpu_baseline(frames, 1)
+    base, dt = cpu_baseline(frames, max(1, args.steps))
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus, args.frames), "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "CPU arm = plain-C port of the reference's Python model (oracle/c/b2j_oracle.c); the model itself "
+                    "is Python-only, cannot travel to the GPU box and measures 0.069 Mpixel/s (BASELINE.md)"}
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_indices):
+        self.gpus = set(gpu_indices)
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        clocks, mx, reasons, power = [], [], set(), []
+        for line in self.f:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                idx = int(parts[0])
+                if idx not in self.gpus:
+                    continue
+                clocks.append(float(parts[1]))
+                mx.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if clocks:
+            busy = [c for c, p in zip(clocks, power) if p > 0.5 * max(power)] or clocks
+            out = {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(clocks), "power_w_max": max(power)}
+        return out
+
+
+# ---------------------------------------------------------------------------------- GPU arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import importlib
+    import litejpeg_b200 as lj
+    synth = importlib.import_module("litejpeg_b200.synth")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the encode path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = max(world, 1)
+    frames = args.frames
+
+    # ---- synthetic input (seeded per rank so every GPU has its own batch), pinned on the host
+    host = torch.empty((frames, H, W, 3), dtype=torch.uint8).pin_memory()
+    synth.batch(frames, H, W, CONFIG_IDX + 100 * rank, "photo", unique=min(UNIQUE_FRAMES, frames), out=host)
+    rgb = host.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+
+    L = lj.lib()
+    desc = lj.make_desc(H, W, SUB, frames)
+    geo = lj.geometry(desc)
+    qy, qc = lj.quant_tables(QUALITY)
+    qy_a, qc_a = lj._lib.table_arg(qy), lj._lib.table_arg(qc)
+    zrl = lj._lib.ZRL[ZRL]
+    cap = int(L.b2j_default_out_cap(ctypes.byref(desc)))
+    nblk = frames * geo.blocks_per_frame
+    coefs = torch.empty((nblk, 64), dtype=torch.int16, device=dev)
+    bits = torch.empty((nblk,), dtype=torch.int32, device=dev)
+    offsets = torch.empty((nblk,), dtype=torch.int32, device=dev)
+    total_bits = torch.empty((frames,), dtype=torch.int64, device=dev)
+    scan_ws = torch.empty((L.b2j_scan_workspace_bytes(ctypes.byref(desc)),), dtype=torch.uint8, device=dev)
+    pack_ws = torch.empty((L.b2j_bitpack_workspace_bytes(ctypes.byref(desc), cap),), dtype=torch.uint8, device=dev)
+    out = torch.empty((frames, cap), dtype=torch.uint8, device=dev)
+    sizes = torch.empty((frames,), dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+    dref = ctypes.byref(desc)
+
+    def step(ev=None):
+        """One pass of the hot path: exactly the launches b2j_encode issues, with optional stage events."""
+        if ev: ev[0].record(stream)
+        lj._lib.check(L.b2j_fused_block(rgb.data_ptr(), dref, qy_a, qc_a, coefs.data_ptr(), 0, sp))
+        if ev: ev[1].record(stream)
+        lj._lib.check(L.b2j_block_bits(coefs.data_ptr(), dref, zrl, bits.data_ptr(), sp))
+        if ev: ev[2].record(stream)
+        lj._lib.check(L.b2j_scan(bits.data_ptr(), dref, offsets.data_ptr(), total_bits.data_ptr(), scan_ws.data_ptr(), sp))
+        if ev: ev[3].record(stream)
+        lj._lib.check(L.b2j_bitpack(coefs.data_ptr(), offsets.data_ptr(), total_bits.data_ptr(), dref, qy_a, qc_a, zrl,
+                                    pack_ws.data_ptr(), out.data_ptr(), cap, sizes.data_ptr(), sp))
+        if ev: ev[4].record(stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- correctness guard: the staged sequence equals the one-call path, and frame 0 equals the oracle
+    step()
+    torch.cuda.synchronize()
+    sz = sizes.cpu()
+    assert int(sz.min()) > 0, "a frame did not fit its output slot"
+    enc = lj.JpegEncoder(SUB, quality=QUALITY, zrl=ZRL)
+    out2, sz2 = enc.encode_device(rgb)
+    torch.cuda.synchronize()
+    assert torch.equal(sz2.cpu(), sz) and torch.equal(out2[0, :int(sz[0])], out[0, :int(sz[0])])
+    del out2, sz2
+    enc._ws = {}
+    torch.cuda.empty_cache()
+    out_bytes = int(sz.sum())
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler([local_rank] if world > 1 else [torch.cuda.current_device()]) if rank == 0 else None
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    barrier()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record(stream)
+    for k in range(args.steps):
+        step(evs[k])
+    t_end.record(stream)
+    barrier()
+    elapsed_ms = t_start.elapsed_time(t_end)
+    stage_ms = [sum(e[i].elapsed_time(e[i + 1]) for e in evs) / args.steps for i in range(4)]
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    px_per_step = n_gpus * frames * H * W
+    value = px_per_step * args.steps / (elapsed_ms / 1e3) / 1e6
+
+    # ---- end to end through the host-buffer entry point of the C ABI
+    e2e = None
+    if not args.skip_e2e:
+        out_host = torch.empty((frames, cap), dtype=torch.uint8).pin_memory()
+        sizes_host = torch.empty((frames,), dtype=torch.int64)
+        henc = lj.JpegEncoder(SUB, quality=QUALITY, zrl=ZRL, out_cap=cap)
+        fpc = 16
+        for _ in range(2):
+            henc.encode_host(host, out_host, sizes_host, frames_per_chunk=fpc)
+        assert torch.equal(sizes_host, sz)
+        assert out_host[frames - 1, :int(sz[-1])].equal(out[frames - 1, :int(sz[-1])].cpu())
+        e_steps = max(3, min(args.steps, 10))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            henc.encode_host(host, out_host, sizes_host, frames_per_chunk=fpc)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": px_per_step * e_steps / dt / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": n_gpus * frames * H * W * 3, "d2h_bytes_per_step": n_gpus * (frames * cap + frames * 8),
+               "steps": e_steps, "ms_per_step": dt / e_steps * 1e3, "frames_per_chunk": fpc,
+               "api": "b2j_encoder_encode_host (pinned host RGB in, JFIF bytes in pinned host memory out; wall clock "
+                      "around the call, which returns when the last byte is on the host)"}
+        henc.close()
+    clocks = sampler.stop() if sampler else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (K1)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    padded_px = frames * geo.padded_width * geo.padded_height
+    k1_bytes = padded_px * 6                      # 3 B/px RGB read + 1.5 coefficients/px * 2 B written (4:2:0)
+    k1_ms = stage_ms[0]
+    achieved = k1_bytes / (k1_ms / 1e3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
+    except Exception:
+        pass
+    roofline = {"kernel": "k_fused_tiled<2,2> (K1: colour + 4:2:0 + float64 DCT + quantise + zig-zag)",
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                "algorithmic_bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms,
+                "traffic": traffic["bytes_per_launch"] if traffic else None,
+                "traffic_source": traffic.get("source") if traffic else None,
+                "share_of_step": k1_ms / sum(stage_ms),
+                "note": "K1 is issue-bound, not HBM-bound: the model's float64 DCT graph costs ~650 FP64-pipe and ~1400 "
+                        "other instructions per 8x8 block-equivalent (DESIGN.md)"}
+
+    base = None
+    if not args.skip_cpu_baseline:
+        base, _ = cpu_baseline(host, 1)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(n_gpus, frames),
+            "stage_ms": {"K1_fused_block": stage_ms[0], "K2_block_bits": stage_ms[1], "K3_scan": stage_ms[2],
+                         "K4_bitpack_stuff": stage_ms[3]},
+            "output_bytes_per_step": out_bytes, "bits_per_pixel": out_bytes * 8 / (frames * H * W),
+            "roofline": roofline, "cpu_baseline": base, "e2e": e2e,
+            "gpu_launches": args.steps * int(L.b2j_encode_launch_count(dref)), "clocks": clocks}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -48,6 +48,8 @@ class RGB2YCbCr:
         if rgb.shape[-1] != 3:
             raise ValueError("last dimension must be 3 (r, g, b)")
         n = rgb.numel() // 3
+        if n == 0:
+            return Packet() if packet else rgb.clone()
         planes = torch.empty((3, n), dtype=torch.uint8, device=rgb.device)
         with torch.cuda.device(rgb.device):
             _lib.check(_lib.lib().b2j_rgb2ycbcr(rgb.data_ptr(), planes[0].data_ptr(), planes[1].data_ptr(),

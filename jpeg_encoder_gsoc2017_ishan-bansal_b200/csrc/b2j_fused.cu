@@ -242,9 +242,9 @@ __device__ __forceinline__ TileCoord tile_coord(const FusedParams &P, long long 
     return c;
 }
 
-// colour conversion of one pixel taken from a 24-byte group (8 pixels)
+// one pixel of a 12-byte group (4 pixels, 3 little-endian words)
 template <int I>
-__device__ __forceinline__ void px_from_group(const uint32_t (&w)[6], uint32_t &r, uint32_t &g, uint32_t &b)
+__device__ __forceinline__ void px_from_group(const uint32_t (&w)[3], uint32_t &r, uint32_t &g, uint32_t &b)
 {
     constexpr int j0 = 3 * I, j1 = 3 * I + 1, j2 = 3 * I + 2;
     r = (w[j0 >> 2] >> (8 * (j0 & 3))) & 0xFFu;
@@ -262,6 +262,17 @@ __device__ __forceinline__ Ycc convert(uint32_t r, uint32_t g, uint32_t b)
     if ((sy & B2J_CONST_EXC_MASK) == 0u) o.y = csc_y_fp64(r, g, b);
     if ((scr & B2J_CONST_EXC_MASK) == 0u) o.cr -= cr_exception(r, g);
     return o;
+}
+
+__device__ __forceinline__ void convert4(const uint8_t *p, Ycc (&o)[4])
+{
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(p);
+    const uint32_t w[3] = {q[0], q[1], q[2]};
+    uint32_t r, g, b;
+    px_from_group<0>(w, r, g, b); o[0] = convert(r, g, b);
+    px_from_group<1>(w, r, g, b); o[1] = convert(r, g, b);
+    px_from_group<2>(w, r, g, b); o[2] = convert(r, g, b);
+    px_from_group<3>(w, r, g, b); o[3] = convert(r, g, b);
 }
 
 template <int H, int V>
@@ -332,80 +343,36 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused_tiled(const __grid_consta
             __syncthreads();
         }
 
-        // ---------------- phase A: colour conversion + subsampling into 8-bit planes
-        // thread `tid` owns the 8-pixel column group `tid` of every row (pair)
-        if (tid * 8 < cur.need_px) {
+        // ---------------- phase A: colour conversion + subsampling into 8-bit planes.
+        // work item = 4 consecutive pixels of one row (4:2:0: of a pair of rows); 8 x 256 items per tile
 #pragma unroll 1
-            for (int ry = 0; ry < 8; ry++) {
-                uint32_t wa[6], wb[6];
-                {
-                    const uint2 *p = reinterpret_cast<const uint2 *>(raw + (ry * V) * kRawPitch + tid * 24);
-                    uint2 a = p[0], b = p[1], c = p[2];
-                    wa[0] = a.x; wa[1] = a.y; wa[2] = b.x; wa[3] = b.y; wa[4] = c.x; wa[5] = c.y;
-                }
+        for (int item = tid; item < 8 * (kTileW / 4); item += kThreads) {
+            const int ry = item / (kTileW / 4), grp = item % (kTileW / 4);
+            if (grp * 4 >= cur.need_px) continue;
+            Ycc A[4], B[4];
+            convert4(raw + (ry * V) * kRawPitch + grp * 12, A);
+            *reinterpret_cast<uint32_t *>(s_y + (ry * V) * kTileW + grp * 4) =
+                A[0].y | (A[1].y << 8) | (A[2].y << 16) | (A[3].y << 24);
+            if (V == 2) {
+                convert4(raw + (ry * 2 + 1) * kRawPitch + grp * 12, B);
+                *reinterpret_cast<uint32_t *>(s_y + (ry * 2 + 1) * kTileW + grp * 4) =
+                    B[0].y | (B[1].y << 8) | (B[2].y << 16) | (B[3].y << 24);
+            }
+            if (H == 1) {
+                *reinterpret_cast<uint32_t *>(s_cb + ry * TS::kCW + grp * 4) =
+                    A[0].cb | (A[1].cb << 8) | (A[2].cb << 16) | (A[3].cb << 24);
+                *reinterpret_cast<uint32_t *>(s_cr + ry * TS::kCW + grp * 4) =
+                    A[0].cr | (A[1].cr << 8) | (A[2].cr << 16) | (A[3].cr << 24);
+            } else {
+                // pair mean (c0 + c1) >> 1 horizontally (crs.py:39-54), then vertically
+                uint32_t cb0 = (A[0].cb + A[1].cb) >> 1, cb1 = (A[2].cb + A[3].cb) >> 1;
+                uint32_t cr0 = (A[0].cr + A[1].cr) >> 1, cr1 = (A[2].cr + A[3].cr) >> 1;
                 if (V == 2) {
-                    const uint2 *p = reinterpret_cast<const uint2 *>(raw + (ry * 2 + 1) * kRawPitch + tid * 24);
-                    uint2 a = p[0], b = p[1], c = p[2];
-                    wb[0] = a.x; wb[1] = a.y; wb[2] = b.x; wb[3] = b.y; wb[4] = c.x; wb[5] = c.y;
+                    cb0 = (cb0 + ((B[0].cb + B[1].cb) >> 1)) >> 1; cb1 = (cb1 + ((B[2].cb + B[3].cb) >> 1)) >> 1;
+                    cr0 = (cr0 + ((B[0].cr + B[1].cr) >> 1)) >> 1; cr1 = (cr1 + ((B[2].cr + B[3].cr) >> 1)) >> 1;
                 }
-                Ycc A[8], B[8];
-                {
-                    uint32_t r, g, b;
-                    px_from_group<0>(wa, r, g, b); A[0] = convert(r, g, b);
-                    px_from_group<1>(wa, r, g, b); A[1] = convert(r, g, b);
-                    px_from_group<2>(wa, r, g, b); A[2] = convert(r, g, b);
-                    px_from_group<3>(wa, r, g, b); A[3] = convert(r, g, b);
-                    px_from_group<4>(wa, r, g, b); A[4] = convert(r, g, b);
-                    px_from_group<5>(wa, r, g, b); A[5] = convert(r, g, b);
-                    px_from_group<6>(wa, r, g, b); A[6] = convert(r, g, b);
-                    px_from_group<7>(wa, r, g, b); A[7] = convert(r, g, b);
-                    if (V == 2) {
-                        px_from_group<0>(wb, r, g, b); B[0] = convert(r, g, b);
-                        px_from_group<1>(wb, r, g, b); B[1] = convert(r, g, b);
-                        px_from_group<2>(wb, r, g, b); B[2] = convert(r, g, b);
-                        px_from_group<3>(wb, r, g, b); B[3] = convert(r, g, b);
-                        px_from_group<4>(wb, r, g, b); B[4] = convert(r, g, b);
-                        px_from_group<5>(wb, r, g, b); B[5] = convert(r, g, b);
-                        px_from_group<6>(wb, r, g, b); B[6] = convert(r, g, b);
-                        px_from_group<7>(wb, r, g, b); B[7] = convert(r, g, b);
-                    }
-                }
-                // luma
-                {
-                    uint2 o;
-                    o.x = A[0].y | (A[1].y << 8) | (A[2].y << 16) | (A[3].y << 24);
-                    o.y = A[4].y | (A[5].y << 8) | (A[6].y << 16) | (A[7].y << 24);
-                    *reinterpret_cast<uint2 *>(s_y + (ry * V) * kTileW + tid * 8) = o;
-                    if (V == 2) {
-                        o.x = B[0].y | (B[1].y << 8) | (B[2].y << 16) | (B[3].y << 24);
-                        o.y = B[4].y | (B[5].y << 8) | (B[6].y << 16) | (B[7].y << 24);
-                        *reinterpret_cast<uint2 *>(s_y + (ry * 2 + 1) * kTileW + tid * 8) = o;
-                    }
-                }
-                // chroma: pair mean (c0 + c1) >> 1 horizontally (crs.py:39-54), then vertically
-                if (H == 1) {
-                    uint2 o;
-                    o.x = A[0].cb | (A[1].cb << 8) | (A[2].cb << 16) | (A[3].cb << 24);
-                    o.y = A[4].cb | (A[5].cb << 8) | (A[6].cb << 16) | (A[7].cb << 24);
-                    *reinterpret_cast<uint2 *>(s_cb + ry * TS::kCW + tid * 8) = o;
-                    o.x = A[0].cr | (A[1].cr << 8) | (A[2].cr << 16) | (A[3].cr << 24);
-                    o.y = A[4].cr | (A[5].cr << 8) | (A[6].cr << 16) | (A[7].cr << 24);
-                    *reinterpret_cast<uint2 *>(s_cr + ry * TS::kCW + tid * 8) = o;
-                } else {
-                    uint32_t ocb = 0u, ocr = 0u;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        uint32_t cb = (A[2 * j].cb + A[2 * j + 1].cb) >> 1, cr = (A[2 * j].cr + A[2 * j + 1].cr) >> 1;
-                        if (V == 2) {
-                            cb = (cb + ((B[2 * j].cb + B[2 * j + 1].cb) >> 1)) >> 1;
-                            cr = (cr + ((B[2 * j].cr + B[2 * j + 1].cr) >> 1)) >> 1;
-                        }
-                        ocb |= cb << (8 * j);
-                        ocr |= cr << (8 * j);
-                    }
-                    *reinterpret_cast<uint32_t *>(s_cb + ry * TS::kCW + tid * 4) = ocb;
-                    *reinterpret_cast<uint32_t *>(s_cr + ry * TS::kCW + tid * 4) = ocr;
-                }
+                *reinterpret_cast<uint16_t *>(s_cb + ry * TS::kCW + grp * 2) = (uint16_t)(cb0 | (cb1 << 8));
+                *reinterpret_cast<uint16_t *>(s_cr + ry * TS::kCW + grp * 2) = (uint16_t)(cr0 | (cr1 << 8));
             }
         }
         __syncthreads();        // planes complete; raw buffer is free again
@@ -419,43 +386,30 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused_tiled(const __grid_consta
             nxt_bulk = issue_load(nxt);
         }
 
-        // ---------------- phase B: one 8x8 block per thread, warp-uniform component class
+        // ---------------- phase B: one 8x8 block per thread, warp-uniform component class,
+        // one code path for luma and chroma (the kernel must fit the instruction cache)
         {
             const int nbx = cur.need_px >> 3;                  // luma blocks per block row
             const int ncx = nbx / H;                           // chroma blocks per component
             const long long mcu_base = ((long long)cur.frame * P.mcus_y + cur.my) * P.mcus_x + cur.x0 / (8 * H);
-            constexpr int kYTasks = V * (kTileW / 8 / 32);     // 32 consecutive blocks of one block row each
-            constexpr int kCTasksPer = kTileW / H / 8 / 32;    // per chroma component
-            constexpr int kTasks = kYTasks + 2 * kCTasksPer;
+            constexpr int kYPer = kTileW / 8 / 32;             // tasks per luma block row
+            constexpr int kYTasks = V * kYPer;
+            constexpr int kCPer = kTileW / H / 8 / 32;         // tasks per chroma component
+            constexpr int kTasks = kYTasks + 2 * kCPer;
 #pragma unroll 1
             for (int task = warp; task < kTasks; task += kThreads / 32) {
-                const uint8_t *plane;
-                int pitch, bx, row0, k;
-                const uint32_t *mul;
-                if (task < kYTasks) {
-                    const int by = task / (kTileW / 8 / 32);
-                    bx = (task % (kTileW / 8 / 32)) * 32 + lane;
-                    if (bx >= nbx) continue;
-                    plane = s_y; pitch = kTileW; row0 = by * 8;
-                    k = by * H + (bx % H);
-                    mul = s_mul;
-                    const long long mcu = mcu_base + bx / H;
-                    uint2 px[8];
-#pragma unroll
-                    for (int i = 0; i < 8; i++) px[i] = *reinterpret_cast<const uint2 *>(plane + (row0 + i) * pitch + bx * 8);
-                    BlockPacker pk;
-                    pk.init(mul);
-                    dct_quant_block(px, pk);
-                    pk.store(P.coefs + (mcu * BPM + k) * 64);
-                } else {
-                    const int ct = task - kYTasks;
-                    const int comp = ct / kCTasksPer;           // 0 = Cb, 1 = Cr
-                    bx = (ct % kCTasksPer) * 32 + lane;
-                    if (bx >= ncx) continue;
-                    plane = comp ? s_cr : s_cb; pitch = TS::kCW;
-                    k = H * V + comp;
-                    mul = s_mul + 64;
-                    const long long mcu = mcu_base + bx;
+                const bool luma = task < kYTasks;
+                const int ct = task - kYTasks;
+                const int by = luma ? task / kYPer : 0;
+                const int comp = luma ? 0 : ct / kCPer;
+                const int bx = (luma ? task % kYPer : ct % kCPer) * 32 + lane;
+                const int nb = luma ? nbx : ncx;
+                const uint8_t *plane = luma ? s_y + by * 8 * kTileW : (comp ? s_cr : s_cb);
+                const int pitch = luma ? kTileW : TS::kCW;
+                const int k = luma ? by * H + (bx % H) : H * V + comp;
+                const long long mcu = mcu_base + (luma ? bx / H : bx);
+                const uint32_t *mul = luma ? s_mul : s_mul + 64;
+                if (bx < nb) {
                     uint2 px[8];
 #pragma unroll
                     for (int i = 0; i < 8; i++) px[i] = *reinterpret_cast<const uint2 *>(plane + i * pitch + bx * 8);
@@ -488,7 +442,10 @@ static int launch_fused(const FusedParams &P, const Geo &g, int variant, cudaStr
     B2J_CUDA(cudaGetDevice(&dev));
     B2J_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     B2J_CUDA(cudaFuncSetAttribute(k_fused_tiled<H, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS::kSmem));
-    const long long grid = n_tiles < 2LL * sms ? n_tiles : 2LL * sms;      // 2 resident CTAs per SM
+    int per_sm = 2;
+    B2J_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_tiled<H, V>, kThreads, TS::kSmem));
+    if (per_sm < 1) per_sm = 1;
+    const long long grid = n_tiles < (long long)per_sm * sms ? n_tiles : (long long)per_sm * sms;   // persistent CTAs
     k_fused_tiled<H, V><<<(unsigned)grid, kThreads, TS::kSmem, st>>>(P, n_tiles, tiles_x);
     B2J_LAUNCH_CHECK("k_fused_tiled");
     return B2J_OK;

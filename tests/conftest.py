@@ -67,7 +67,7 @@ class OracleC:
 
     def block_bits(self, coefs, h, w, sub, zrl):
         coefs = np.ascontiguousarray(coefs, dtype=np.int16)
-        bits = np.zeros(coefs.shape[0] * coefs.shape[1], np.int32)
+        bits = np.zeros(coefs.size // 64, np.int32)
         rc = self.lib.b2jo_block_bits(self._p(coefs), h, w, int(sub), int(zrl), self._p(bits))
         assert rc == 0
         return bits
