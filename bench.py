@@ -6,7 +6,8 @@
 
 Workload (BASELINE.json configs[2], the configuration the Mpixel/s metric is quoted on): per GPU a
 batch of 256 synthetic 1920x1080 RGB frames, 4:2:0, quality 75 -> 256 JFIF files.  One "step" is one
-pass of the whole hot path (K1 fused block kernel, K2 block bits, K3 scan, K4 bit pack + stuffing)
+pass of the whole hot path (K1 fused block kernel; K2-K4 fused entropy kernel: block bits, scan with
+look-back, bit packing; 0xFF stuffing + JFIF framing)
 over that batch.  Frames are independent, so ranks shard by frames with no data-path collective
 (weak scaling: every rank encodes its own 256-frame batch).
 
@@ -219,11 +220,8 @@ def main():
     cap = int(L.b2j_default_out_cap(ctypes.byref(desc)))
     nblk = frames * geo.blocks_per_frame
     coefs = torch.empty((nblk, 64), dtype=torch.int16, device=dev)
-    bits = torch.empty((nblk,), dtype=torch.int32, device=dev)
-    offsets = torch.empty((nblk,), dtype=torch.int32, device=dev)
-    total_bits = torch.empty((frames,), dtype=torch.int64, device=dev)
-    scan_ws = torch.empty((L.b2j_scan_workspace_bytes(ctypes.byref(desc)),), dtype=torch.uint8, device=dev)
-    pack_ws = torch.empty((L.b2j_bitpack_workspace_bytes(ctypes.byref(desc), cap),), dtype=torch.uint8, device=dev)
+    ent_ws = torch.empty((L.b2j_entropy_workspace_bytes(ctypes.byref(desc), cap) + 256,), dtype=torch.uint8, device=dev)
+    ent_ptr = (ent_ws.data_ptr() + 255) & ~255
     out = torch.empty((frames, cap), dtype=torch.uint8, device=dev)
     sizes = torch.empty((frames,), dtype=torch.int64, device=dev)
     stream = torch.cuda.current_stream()
@@ -235,13 +233,9 @@ def main():
         if ev: ev[0].record(stream)
         lj._lib.check(L.b2j_fused_block(rgb.data_ptr(), dref, qy_a, qc_a, coefs.data_ptr(), 0, sp))
         if ev: ev[1].record(stream)
-        lj._lib.check(L.b2j_block_bits(coefs.data_ptr(), dref, zrl, bits.data_ptr(), sp))
+        lj._lib.check(L.b2j_entropy_encode(coefs.data_ptr(), dref, qy_a, qc_a, zrl, ent_ptr, out.data_ptr(), cap,
+                                           sizes.data_ptr(), sp))
         if ev: ev[2].record(stream)
-        lj._lib.check(L.b2j_scan(bits.data_ptr(), dref, offsets.data_ptr(), total_bits.data_ptr(), scan_ws.data_ptr(), sp))
-        if ev: ev[3].record(stream)
-        lj._lib.check(L.b2j_bitpack(coefs.data_ptr(), offsets.data_ptr(), total_bits.data_ptr(), dref, qy_a, qc_a, zrl,
-                                    pack_ws.data_ptr(), out.data_ptr(), cap, sizes.data_ptr(), sp))
-        if ev: ev[4].record(stream)
 
     def barrier():
         if world > 1:
@@ -265,7 +259,7 @@ def main():
     for _ in range(args.warmup):
         step()
     sampler = ClockSampler([local_rank] if world > 1 else [torch.cuda.current_device()]) if rank == 0 else None
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     barrier()
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
@@ -275,7 +269,7 @@ def main():
     t_end.record(stream)
     barrier()
     elapsed_ms = t_start.elapsed_time(t_end)
-    stage_ms = [sum(e[i].elapsed_time(e[i + 1]) for e in evs) / args.steps for i in range(4)]
+    stage_ms = [sum(e[i].elapsed_time(e[i + 1]) for e in evs) / args.steps for i in range(2)]
     if world > 1:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -351,8 +345,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(n_gpus, frames),
-            "stage_ms": {"K1_fused_block": stage_ms[0], "K2_block_bits": stage_ms[1], "K3_scan": stage_ms[2],
-                         "K4_bitpack_stuff": stage_ms[3]},
+            "stage_ms": {"K1_fused_block": stage_ms[0], "K2_K3_K4_entropy_fused_and_stuffing": stage_ms[1]},
             "output_bytes_per_step": out_bytes, "bits_per_pixel": out_bytes * 8 / (frames * H * W),
             "roofline": roofline, "cpu_baseline": base, "e2e": e2e,
             "gpu_launches": args.steps * int(L.b2j_encode_launch_count(dref)), "clocks": clocks}

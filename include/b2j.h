@@ -172,6 +172,16 @@ int b2j_bitpack(const int16_t *coefs, const uint32_t *offsets, const int64_t *to
                 int zrl, void *workspace, uint8_t *out, int64_t out_cap, int64_t *sizes,
                 void *stream);
 
+/* K2 + K3 + K4 fused into one pass over the coefficients (what b2j_encode uses): per chunk of
+ * 128 blocks the sizes are counted, scanned inside the CTA, chained across chunks by a
+ * decoupled look-back, and the bits are packed at their final offsets; 0xFF stuffing, JFIF
+ * header and EOI follow.  Same outputs as b2j_block_bits + b2j_scan + b2j_bitpack.
+ * workspace: b2j_entropy_workspace_bytes() bytes, 256-byte aligned. */
+size_t b2j_entropy_workspace_bytes(const b2j_image_desc *desc, int64_t out_cap);
+int b2j_entropy_encode(const int16_t *coefs, const b2j_image_desc *desc,
+                       const uint8_t qy_host[64], const uint8_t qc_host[64], int zrl,
+                       void *workspace, uint8_t *out, int64_t out_cap, int64_t *sizes, void *stream);
+
 /* The whole path K1..K4 on device buffers.  workspace: b2j_encode_workspace_bytes().
  * quality 1..100 picks the [ext] IJG tables, or pass quality = 0 and explicit
  * tables. */

@@ -58,6 +58,8 @@ SIGNATURES = {
     "b2j_scan": (c_int, [_P, _DESC, _P, _P, _P, _P]),
     "b2j_bitpack_workspace_bytes": (c_size_t, [_DESC, c_int64]),
     "b2j_bitpack": (c_int, [_P, _P, _P, _DESC, _P, _P, c_int, _P, _P, c_int64, _P, _P]),
+    "b2j_entropy_workspace_bytes": (c_size_t, [_DESC, c_int64]),
+    "b2j_entropy_encode": (c_int, [_P, _DESC, _P, _P, c_int, _P, _P, c_int64, _P, _P]),
     "b2j_encode_workspace_bytes": (c_size_t, [_DESC, c_int64]),
     "b2j_default_out_cap": (c_int64, [_DESC]),
     "b2j_encode": (c_int, [_P, _DESC, c_int, _P, _P, c_int, _P, c_size_t, _P, c_int64, _P, _P]),

@@ -11,7 +11,7 @@ namespace {
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
-    size_t coefs, bits, offsets, total_bits, scan_ws, pack_ws, total;
+    size_t coefs, entropy_ws, total;
 };
 
 int ws_layout(const b2j_image_desc *desc, int64_t out_cap, WsLayout *w)
@@ -24,11 +24,7 @@ int ws_layout(const b2j_image_desc *desc, int64_t out_cap, WsLayout *w)
     const size_t nb = (size_t)g.n_frames * (size_t)g.blocks_per_frame;
     size_t o = 0;
     w->coefs = o; o = align_up(o + nb * 64 * sizeof(int16_t), 256);
-    w->bits = o; o = align_up(o + nb * sizeof(int32_t), 256);
-    w->offsets = o; o = align_up(o + nb * sizeof(uint32_t), 256);
-    w->total_bits = o; o = align_up(o + (size_t)g.n_frames * sizeof(int64_t), 256);
-    w->scan_ws = o; o = align_up(o + b2j_scan_workspace_bytes(desc), 256);
-    w->pack_ws = o; o = align_up(o + b2j_bitpack_workspace_bytes(desc, out_cap), 256);
+    w->entropy_ws = o; o = align_up(o + b2j_entropy_workspace_bytes(desc, out_cap), 256);
     w->total = o;
     return B2J_OK;
 }
@@ -55,7 +51,7 @@ extern "C" size_t b2j_encode_workspace_bytes(const b2j_image_desc *desc, int64_t
 extern "C" int b2j_encode_launch_count(const b2j_image_desc *desc)
 {
     (void)desc;
-    return 9;   // fused_block, block_bits, 3 x scan, bitpack, ff_count, ff_scan, stuff_write
+    return 5;   // k_fused_tiled, k_entropy_fused, k_ff_count, k_ff_scan, k_stuff_write (+ one small memset)
 }
 
 extern "C" int b2j_encode(const uint8_t *rgb, const b2j_image_desc *desc, int quality, const uint8_t qy_host[64],
@@ -79,13 +75,8 @@ extern "C" int b2j_encode(const uint8_t *rgb, const b2j_image_desc *desc, int qu
     B2J_REQUIRE(workspace_bytes >= w.total, B2J_E_WORKSPACE, "b2j_encode: workspace %zu < %zu bytes", workspace_bytes, w.total);
     uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
     int16_t *coefs = reinterpret_cast<int16_t *>(ws + w.coefs);
-    int32_t *bits = reinterpret_cast<int32_t *>(ws + w.bits);
-    uint32_t *offsets = reinterpret_cast<uint32_t *>(ws + w.offsets);
-    int64_t *total_bits = reinterpret_cast<int64_t *>(ws + w.total_bits);
     if ((rc = b2j_fused_block(rgb, desc, qy, qc, coefs, B2J_FUSED_AUTO, stream))) return rc;
-    if ((rc = b2j_block_bits(coefs, desc, zrl, bits, stream))) return rc;
-    if ((rc = b2j_scan(bits, desc, offsets, total_bits, ws + w.scan_ws, stream))) return rc;
-    if ((rc = b2j_bitpack(coefs, offsets, total_bits, desc, qy, qc, zrl, ws + w.pack_ws, out, out_cap, sizes, stream))) return rc;
+    if ((rc = b2j_entropy_encode(coefs, desc, qy, qc, zrl, ws + w.entropy_ws, out, out_cap, sizes, stream))) return rc;
     return B2J_OK;
 }
 

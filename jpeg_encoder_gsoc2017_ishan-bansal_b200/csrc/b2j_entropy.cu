@@ -15,92 +15,9 @@
 //
 // The same block walker produces the sizes (K2) and the bits (K4), so scanned
 // offsets and emitted lengths cannot disagree.
-#include "b2j_common.cuh"
-#include "b2j_math.cuh"
+#include "b2j_entropy.cuh"
 
 namespace b2j {
-
-struct EGeo {
-    int hv, bpm;                  // luma blocks per MCU, blocks per MCU
-    int n_frames;
-    long long nblk;               // blocks per frame
-};
-
-static EGeo egeo_of(const Geo &g)
-{
-    EGeo e;
-    e.hv = g.h * g.v; e.bpm = g.bpm; e.n_frames = g.n_frames; e.nblk = g.blocks_per_frame;
-    return e;
-}
-
-struct LutParam { HuffLut lut; };
-
-__device__ __forceinline__ void load_lut(const LutParam &L, uint32_t *s_dc /*[2][16]*/, uint32_t *s_ac /*[2][256]*/)
-{
-    for (int i = threadIdx.x; i < 32; i += blockDim.x) s_dc[i] = L.lut.dc[i >> 4][i & 15];
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_ac[i] = L.lut.ac[i >> 8][i & 255];
-}
-
-// DC of the previous block of the same component inside the frame (0 if none).
-__device__ __forceinline__ int prev_dc(const int16_t *frame_coefs, long long b, const EGeo &e)
-{
-    const int k = (int)(b % e.bpm);
-    long long p;
-    if (k < e.hv) p = k > 0 ? b - 1 : b - e.bpm + e.hv - 1;
-    else p = b - e.bpm;
-    return p >= 0 ? (int)frame_coefs[p * 64] : 0;
-}
-
-// Walks one block in zig-zag order and hands every coded field to sink.put(value, nbits).
-template <bool EAGER, class Sink>
-__device__ __forceinline__ void walk_block(const int16_t *__restrict__ c, int diff, const uint32_t *__restrict__ lut_dc,
-                                           const uint32_t *__restrict__ lut_ac, Sink &sink)
-{
-    {
-        const int s = bit_size(diff);
-        const uint32_t e = lut_dc[s];
-        const uint32_t extra = (uint32_t)(diff < 0 ? diff - 1 : diff) & ((1u << s) - 1u);
-        sink.put(((e & 0xFFFFu) << s) | extra, (int)(e >> 16) + s);
-    }
-    const uint32_t zrl = lut_ac[0xF0], eob = lut_ac[0x00];
-    int run = 0;
-    const uint4 *c4 = reinterpret_cast<const uint4 *>(c);
-#pragma unroll 1
-    for (int i = 0; i < 8; i++) {
-        const uint4 q = __ldg(c4 + i);
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int k = i * 8 + j;
-            if (k == 0) continue;
-            const int v = (int)(int16_t)(w[j >> 1] >> (16 * (j & 1)));
-            uint32_t val = 0u;
-            int len = 0;
-            if (v != 0) {
-                if (!EAGER) {
-                    while (run > 15) { sink.put(zrl & 0xFFFFu, (int)(zrl >> 16)); run -= 16; }
-                }
-                const int s = bit_size(v);
-                const uint32_t e = lut_ac[(run << 4) | s];
-                val = ((e & 0xFFFFu) << s) | ((uint32_t)(v < 0 ? v - 1 : v) & ((1u << s) - 1u));
-                len = (int)(e >> 16) + s;
-                run = 0;
-            } else if (EAGER && run == 15) {
-                val = zrl & 0xFFFFu; len = (int)(zrl >> 16); run = 0;
-            } else if (k == 63) {
-                val = eob & 0xFFFFu; len = (int)(eob >> 16);
-            } else {
-                run++;
-            }
-            sink.put(val, len);
-        }
-    }
-}
-
-struct CountSink {
-    int bits;
-    __device__ __forceinline__ void put(uint32_t, int len) { bits += len; }
-};
 
 // ---------------------------------------------------------------- K2
 template <bool EAGER>
@@ -124,36 +41,6 @@ __global__ void __launch_bounds__(128) k_block_bits(const int16_t *__restrict__ 
 
 // ---------------------------------------------------------------- K3 (three small kernels)
 constexpr int kScanChunk = 1024;          // blocks per scan chunk (256 threads x 4)
-
-__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v)
-{
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t n = __shfl_up_sync(0xffffffffu, v, d);
-        if (lane >= d) v += n;
-    }
-    return v;
-}
-
-// exclusive scan over the CTA (256 threads); returns exclusive prefix, *total = CTA sum
-__device__ __forceinline__ uint32_t cta_excl_scan_256(uint32_t v, uint32_t *s_warp /*[8]*/, uint32_t *total)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t inc = warp_incl_scan(v);
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    uint32_t base = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < 8; w++) {
-        const uint32_t x = s_warp[w];
-        if (w < warp) base += x;
-        tot += x;
-    }
-    __syncthreads();
-    *total = tot;
-    return base + inc - v;
-}
 
 __global__ void __launch_bounds__(256) k_chunk_sums(const int32_t *__restrict__ bits, uint32_t *__restrict__ partial,
                                                     long long nblk, int chunks)
@@ -292,7 +179,6 @@ __global__ void __launch_bounds__(kPackBlocks) k_bitpack(const int16_t *__restri
 }
 
 // ---------------------------------------------------------------- K4b: 0xFF stuffing + framing
-constexpr int kStuffChunk = 4096;         // unstuffed bytes per CTA (256 threads x 16)
 
 __device__ __forceinline__ uint32_t ff_mask16(const uint4 &q, int nvalid)
 {
@@ -324,7 +210,7 @@ __global__ void __launch_bounds__(256) k_ff_count(const uint8_t *__restrict__ un
 // one CTA per frame: exclusive scan of 0xFF counts; final size / capacity verdict
 __global__ void __launch_bounds__(256) k_ff_scan(uint32_t *__restrict__ ffpart, const int64_t *__restrict__ total_bits,
                                                  int64_t *__restrict__ sizes, long long ucap, long long out_cap, int chunks,
-                                                 int header_bytes)
+                                                 int header_bytes, const int *__restrict__ error_flag)
 {
     __shared__ uint32_t s_warp[8];
     uint32_t *p = ffpart + (long long)blockIdx.x * chunks;
@@ -339,7 +225,8 @@ __global__ void __launch_bounds__(256) k_ff_scan(uint32_t *__restrict__ ffpart, 
     }
     if (threadIdx.x == 0) {
         const long long nbytes = (total_bits[blockIdx.x] + 7) >> 3;
-        if (nbytes > ucap) sizes[blockIdx.x] = -(header_bytes + 2 * nbytes + 2);      // upper bound of the need
+        if (error_flag && *error_flag) sizes[blockIdx.x] = (int64_t)0x8000000000000000LL;     // internal error
+        else if (nbytes > ucap) sizes[blockIdx.x] = -(header_bytes + 2 * nbytes + 2);      // upper bound of the need
         else {
             const long long need = header_bytes + nbytes + (long long)carry + 2;
             sizes[blockIdx.x] = need <= out_cap ? need : -need;
@@ -347,7 +234,6 @@ __global__ void __launch_bounds__(256) k_ff_scan(uint32_t *__restrict__ ffpart, 
     }
 }
 
-struct HeaderParam { uint8_t bytes[kHeaderBytes + 1]; };
 
 __global__ void __launch_bounds__(256) k_stuff_write(const uint8_t *__restrict__ unstuffed, const int64_t *__restrict__ total_bits,
                                                      const uint32_t *__restrict__ ffpart, const int64_t *__restrict__ sizes,
@@ -409,14 +295,22 @@ __global__ void __launch_bounds__(256) k_stuff_write(const uint8_t *__restrict__
     }
 }
 
-static LutParam make_lut_param()
-{
-    LutParam L;
-    L.lut = host_huff_lut();
-    return L;
-}
-
 static int scan_chunks(long long nblk) { return (int)((nblk + kScanChunk - 1) / kScanChunk); }
+
+int launch_stuffing(const uint8_t *unstuffed, const int64_t *total_bits, uint32_t *ffpart, int64_t *sizes, uint8_t *out,
+                    long long ucap, long long out_cap, int n_frames, const HeaderParam &H, const int *error_flag,
+                    cudaStream_t st)
+{
+    const int schunks = stuff_chunks(ucap);
+    dim3 sgrid((unsigned)schunks, (unsigned)n_frames);
+    k_ff_count<<<sgrid, 256, 0, st>>>(unstuffed, total_bits, ffpart, ucap, schunks);
+    B2J_LAUNCH_CHECK("k_ff_count");
+    k_ff_scan<<<(unsigned)n_frames, 256, 0, st>>>(ffpart, total_bits, sizes, ucap, out_cap, schunks, kHeaderBytes, error_flag);
+    B2J_LAUNCH_CHECK("k_ff_scan");
+    k_stuff_write<<<sgrid, 256, 0, st>>>(unstuffed, total_bits, ffpart, sizes, out, ucap, out_cap, schunks, H);
+    B2J_LAUNCH_CHECK("k_stuff_write");
+    return B2J_OK;
+}
 
 }  // namespace b2j
 
@@ -467,8 +361,6 @@ extern "C" int b2j_scan(const int32_t *bits, const b2j_image_desc *desc, uint32_
     return B2J_OK;
 }
 
-static long long ucap_of(int64_t out_cap) { return ((long long)out_cap + 15) & ~15LL; }
-static int stuff_chunks(long long ucap) { return (int)((ucap + kStuffChunk - 1) / kStuffChunk); }
 
 extern "C" size_t b2j_bitpack_workspace_bytes(const b2j_image_desc *desc, int64_t out_cap)
 {
@@ -493,7 +385,6 @@ extern "C" int b2j_bitpack(const int16_t *coefs, const uint32_t *offsets, const 
     if (rc) return rc;
     const EGeo e = egeo_of(g);
     const long long ucap = ucap_of(out_cap);
-    const int schunks = stuff_chunks(ucap);
     uint8_t *unstuffed = reinterpret_cast<uint8_t *>(workspace);
     uint32_t *ffpart = reinterpret_cast<uint32_t *>(unstuffed + (size_t)g.n_frames * (size_t)ucap);
     HeaderParam H;
@@ -508,12 +399,5 @@ extern "C" int b2j_bitpack(const int16_t *coefs, const uint32_t *offsets, const 
     if (zrl == B2J_ZRL_EAGER) k_bitpack<true><<<pgrid, kPackBlocks, 0, st>>>(coefs, offsets, total_bits, unstuffed, ucap, e, L);
     else k_bitpack<false><<<pgrid, kPackBlocks, 0, st>>>(coefs, offsets, total_bits, unstuffed, ucap, e, L);
     B2J_LAUNCH_CHECK("k_bitpack");
-    dim3 sgrid((unsigned)schunks, (unsigned)g.n_frames);
-    k_ff_count<<<sgrid, 256, 0, st>>>(unstuffed, total_bits, ffpart, ucap, schunks);
-    B2J_LAUNCH_CHECK("k_ff_count");
-    k_ff_scan<<<(unsigned)g.n_frames, 256, 0, st>>>(ffpart, total_bits, sizes, ucap, out_cap, schunks, kHeaderBytes);
-    B2J_LAUNCH_CHECK("k_ff_scan");
-    k_stuff_write<<<sgrid, 256, 0, st>>>(unstuffed, total_bits, ffpart, sizes, out, ucap, out_cap, schunks, H);
-    B2J_LAUNCH_CHECK("k_stuff_write");
-    return B2J_OK;
+    return launch_stuffing(unstuffed, total_bits, ffpart, sizes, out, ucap, out_cap, g.n_frames, H, nullptr, st);
 }

@@ -219,7 +219,7 @@ struct TileShape {
     static constexpr int kRawBytes = kRows * kRawPitch;
     static constexpr int kYBytes = kRows * kTileW;
     static constexpr int kCBytes = 8 * kCW;
-    static constexpr int kSmem = kRawBytes + kYBytes + 2 * kCBytes + 2 * 64 * 4 + 16;
+    static constexpr int kSmem = kRawBytes + kYBytes + 2 * kCBytes + 2 * 64 * 4 + 256 + 16;
 };
 
 struct TileCoord {
@@ -254,25 +254,29 @@ __device__ __forceinline__ void px_from_group(const uint32_t (&w)[3], uint32_t &
 
 struct Ycc { uint32_t y, cb, cr; };
 
-__device__ __forceinline__ Ycc convert(uint32_t r, uint32_t g, uint32_t b)
+// crx: 256-entry shared-memory table of cr_exception_class(g).  Cr candidates (g == b with
+// r - g even) are common in real images, so they only cost one predicated table read; the
+// branch is taken for the eight special grey levels only.
+__device__ __forceinline__ Ycc convert(uint32_t r, uint32_t g, uint32_t b, const uint8_t *crx)
 {
     const uint32_t sy = csc_sum_y(r, g, b), scb = csc_sum_cb(r, g, b), scr = csc_sum_cr(r, g, b);
     Ycc o;
     o.y = sy >> 24; o.cb = scb >> 24; o.cr = scr >> 24;
+    const uint32_t cls = (scr & B2J_CONST_EXC_MASK) == 0u ? (uint32_t)crx[g] : 0u;
     if ((sy & B2J_CONST_EXC_MASK) == 0u) o.y = csc_y_fp64(r, g, b);
-    if ((scr & B2J_CONST_EXC_MASK) == 0u) o.cr -= cr_exception(r, g);
+    if (cls != 0u) o.cr -= cr_exception_apply(cls, r, g);
     return o;
 }
 
-__device__ __forceinline__ void convert4(const uint8_t *p, Ycc (&o)[4])
+__device__ __forceinline__ void convert4(const uint8_t *p, Ycc (&o)[4], const uint8_t *crx)
 {
     const uint32_t *q = reinterpret_cast<const uint32_t *>(p);
     const uint32_t w[3] = {q[0], q[1], q[2]};
     uint32_t r, g, b;
-    px_from_group<0>(w, r, g, b); o[0] = convert(r, g, b);
-    px_from_group<1>(w, r, g, b); o[1] = convert(r, g, b);
-    px_from_group<2>(w, r, g, b); o[2] = convert(r, g, b);
-    px_from_group<3>(w, r, g, b); o[3] = convert(r, g, b);
+    px_from_group<0>(w, r, g, b); o[0] = convert(r, g, b, crx);
+    px_from_group<1>(w, r, g, b); o[1] = convert(r, g, b, crx);
+    px_from_group<2>(w, r, g, b); o[2] = convert(r, g, b, crx);
+    px_from_group<3>(w, r, g, b); o[3] = convert(r, g, b, crx);
 }
 
 template <int H, int V>
@@ -286,10 +290,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused_tiled(const __grid_consta
     uint8_t *s_cb = s_y + TS::kYBytes;
     uint8_t *s_cr = s_cb + TS::kCBytes;
     uint32_t *s_mul = reinterpret_cast<uint32_t *>(s_cr + TS::kCBytes);      // [2][64]
-    uint64_t *bar = reinterpret_cast<uint64_t *>(s_mul + 128);
+    uint8_t *s_crx = reinterpret_cast<uint8_t *>(s_mul + 128);               // [256]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(s_crx + 256);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     s_mul[tid] = P.qm.mul[tid >> 6][tid & 63];
+    s_crx[tid] = (uint8_t)cr_exception_class((uint32_t)tid);
+    s_crx[tid + 128] = (uint8_t)cr_exception_class((uint32_t)tid + 128u);
     if (tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -350,11 +357,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused_tiled(const __grid_consta
             const int ry = item / (kTileW / 4), grp = item % (kTileW / 4);
             if (grp * 4 >= cur.need_px) continue;
             Ycc A[4], B[4];
-            convert4(raw + (ry * V) * kRawPitch + grp * 12, A);
+            convert4(raw + (ry * V) * kRawPitch + grp * 12, A, s_crx);
             *reinterpret_cast<uint32_t *>(s_y + (ry * V) * kTileW + grp * 4) =
                 A[0].y | (A[1].y << 8) | (A[2].y << 16) | (A[3].y << 24);
             if (V == 2) {
-                convert4(raw + (ry * 2 + 1) * kRawPitch + grp * 12, B);
+                convert4(raw + (ry * 2 + 1) * kRawPitch + grp * 12, B, s_crx);
                 *reinterpret_cast<uint32_t *>(s_y + (ry * 2 + 1) * kTileW + grp * 4) =
                     B[0].y | (B[1].y << 8) | (B[2].y << 16) | (B[3].y << 24);
             }

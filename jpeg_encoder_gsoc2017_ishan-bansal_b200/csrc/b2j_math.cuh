@@ -69,15 +69,26 @@ static __device__ __noinline__ uint32_t csc_y_fp64(uint32_t r, uint32_t g, uint3
     return (uint32_t)__double2int_rz(t);
 }
 
-// 1 when the float64 model yields Cr one below the exact value.  Only valid for
-// candidates (g == b, r - g even).  The eight grey levels and the r ranges are
-// the complete list (tests/test_kernel_identities.py).
+// Where the float64 model yields Cr one below the exact value.  Only candidates
+// (g == b, r - g even) can differ, and only at eight grey levels g:
+//   class 1 (g = 201, 213, 225, 237, 249): every candidate with r <= g;
+//   class 2 (g = 164, 176, 188): candidates with r <= g - 128 or g - 30 <= r <= g.
+// That is the complete list of the 688 inputs (tests/test_kernel_identities.py).
+__device__ __forceinline__ uint32_t cr_exception_class(uint32_t g)
+{
+    if (g == 201u || g == 213u || g == 225u || g == 237u || g == 249u) return 1u;
+    if (g == 164u || g == 176u || g == 188u) return 2u;
+    return 0u;
+}
+__device__ __forceinline__ uint32_t cr_exception_apply(uint32_t cls, uint32_t r, uint32_t g)
+{
+    if (r > g) return 0u;
+    return cls == 1u ? 1u : ((r + 128u <= g || r + 30u >= g) ? 1u : 0u);
+}
 __device__ __forceinline__ uint32_t cr_exception(uint32_t r, uint32_t g)
 {
-    if (g < 164u || r > g) return 0u;
-    if (g == 201u || g == 213u || g == 225u || g == 237u || g == 249u) return 1u;
-    if (g == 164u || g == 176u || g == 188u) return (r + 128u <= g || r + 30u >= g) ? 1u : 0u;
-    return 0u;
+    const uint32_t cls = cr_exception_class(g);
+    return cls ? cr_exception_apply(cls, r, g) : 0u;
 }
 
 // Full per-pixel conversion; returns Y | Cb << 8 | Cr << 16.

@@ -73,6 +73,18 @@ def test_stagewise_entropy_path(lj, oracle_c, golden, sub, zrl):
         n = int(sizes[f])
         assert n == len(ref)
         assert out[f, :n].cpu().numpy().tobytes() == ref
+    # the fused single-pass entropy kernel (what b2j_encode uses) gives the same files
+    L = lj.lib()
+    cap = out.shape[1]
+    ws = torch.empty((L.b2j_entropy_workspace_bytes(ctypes.byref(desc), cap) + 256,), dtype=torch.uint8, device="cuda")
+    out2 = torch.zeros_like(out)
+    sizes2 = torch.zeros_like(sizes)
+    lj._lib.check(L.b2j_entropy_encode(coefs.data_ptr(), ctypes.byref(desc), lj._lib.table_arg(enc.qy), lj._lib.table_arg(enc.qc),
+                                       zi, (ws.data_ptr() + 255) & ~255, out2.data_ptr(), cap, sizes2.data_ptr(),
+                                       torch.cuda.current_stream().cuda_stream))
+    assert torch.equal(sizes2, sizes)
+    for f in range(2):
+        assert torch.equal(out2[f, :int(sizes[f])], out[f, :int(sizes[f])])
 
 
 @pytest.mark.parametrize("sub", SUBS)
