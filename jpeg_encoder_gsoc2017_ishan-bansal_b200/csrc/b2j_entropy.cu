@@ -196,6 +196,10 @@ __global__ void __launch_bounds__(256) k_ff_count(const uint8_t *__restrict__ un
     __shared__ uint32_t s_warp[8];
     const int f = blockIdx.y, ch = blockIdx.x;
     const long long nbytes = min((long long)((total_bits[f] + 7) >> 3), ucap);
+    if ((long long)ch * kStuffChunk >= nbytes) {                    // chunk beyond the stream: nothing to count
+        if (threadIdx.x == 0) ffpart[(long long)f * chunks + ch] = 0u;
+        return;
+    }
     const long long pos = (long long)ch * kStuffChunk + threadIdx.x * 16;
     uint32_t cnt = 0;
     if (pos < nbytes) {
@@ -245,6 +249,7 @@ __global__ void __launch_bounds__(256) k_stuff_write(const uint8_t *__restrict__
     const int f = blockIdx.y, ch = blockIdx.x;
     if (sizes[f] < 0) return;                                       // slot too small: leave it untouched
     const long long nbytes = (total_bits[f] + 7) >> 3;
+    if ((long long)ch * kStuffChunk >= nbytes) return;              // chunk beyond the stream
     uint8_t *dst_frame = out + (long long)f * out_cap;
     if (ch == 0)
         for (int i = threadIdx.x; i < kHeaderBytes; i += 256) dst_frame[i] = H.bytes[i];

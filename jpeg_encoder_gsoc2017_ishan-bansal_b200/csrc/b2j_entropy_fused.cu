@@ -2,20 +2,20 @@
 //
 // One CTA per chunk of 128 consecutive blocks of a frame, in launch order (ticket):
 //   1. the chunk's coefficients (+ 8 lookahead blocks) are loaded once, coalesced, into
-//      shared memory (16-byte pieces, XOR-swizzled so that the per-thread reads are
-//      conflict free);
-//   2. every thread takes one block: 64-bit non-zero mask, DC difference, and a SPARSE walk
-//      over the set bits only (symbols as in b2j_entropy.cuh: gateware run-length rules,
-//      Annex-K code lengths) that counts the block's bits;
+//      shared memory (33-word pitch per block: conflict free both for the cooperative
+//      stores and for the per-thread reads); the loading thread also records which of its
+//      eight coefficients are non-zero, so every block gets its 64-bit non-zero mask;
+//   2. every thread takes one block and walks ONLY the set bits of the mask (symbols as in
+//      b2j_entropy.cuh: gateware run-length rules, Annex-K codes), packing the block's bits
+//      MSB-first into a thread-private column of shared memory and counting them;
 //   3. warp-shuffle + CTA exclusive scan of the bit counts; the chunk total is published and
 //      the chunk's bit offset inside the frame is obtained by a decoupled look-back over the
 //      chunk totals of its predecessors (one 64-bit status word per chunk: flag | value);
-//   4. a second sparse walk emits the bits at their final positions into a shared-memory
-//      window (32-bit words, MSB first); the chunk owns every 32-bit word of the stream whose
-//      first bit it contains and completes its last owned word by also emitting the first
-//      bits of the next few blocks (lookahead), so all global stores are plain, coalesced,
-//      full-word stores - no global atomics, no zero-initialised output;
-//   5. the last chunk of a frame pads the final byte with 1s and writes total_bits[frame].
+//   4. every thread composes the 32-bit words of the frame's stream whose first bit lies in
+//      its block: its own private bits shifted to the final alignment, completed with the
+//      first bits of the following blocks (the 8 lookahead blocks cover the chunk's tail).
+//      Every output word has exactly one writer: plain stores, no atomics, no zero-init;
+//   5. the last block of a frame pads the final byte with 1s; total_bits[frame] is written.
 // 0xFF stuffing and JFIF framing then run on the packed stream (launch_stuffing).
 #include "b2j_entropy.cuh"
 
@@ -23,10 +23,12 @@ namespace b2j {
 
 constexpr int kChunk = 128;                       // blocks per CTA == threads per CTA
 constexpr int kLookahead = 8;                     // >= 31 bits / (4 bits per smallest block)
-constexpr int kWinWords = 2048;                   // staging window (65536 bits)
-constexpr int kSlackWords = 64;                   // >= one maximal block (1728 bits)
+constexpr int kCols = kChunk + kLookahead;        // blocks held in shared memory
+constexpr int kPitch = 33;                        // words per block in shared memory (32 + 1 pad)
+constexpr int kPrivWords = 55;                    // >= (1728 + 7 pad bits) / 32 + 1
 constexpr unsigned long long kFlagA = 1ull << 62, kFlagP = 2ull << 62, kValMask = (1ull << 62) - 1;
 constexpr int kSpinLimit = 1 << 22;
+constexpr int kFusedSmem = (kCols * kPitch + kPrivWords * kCols + kCols + kCols * 2 + 32 + 512 + 16) * 4;
 
 struct FusedEntropyParams {
     const int16_t *coefs;
@@ -51,34 +53,39 @@ __device__ __forceinline__ void st_volatile(unsigned long long *p, unsigned long
     asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// coefficient z (zig-zag position) of a block stored as 8 swizzled 16-byte pieces
-__device__ __forceinline__ int coef_at(const uint8_t *blk, int swz, int z)
-{
-    return (int)*reinterpret_cast<const int16_t *>(blk + ((((z >> 3) ^ swz) & 7) << 4) + ((z & 7) << 1));
-}
-
-__device__ __forceinline__ void block_mask(const uint8_t *blk, int swz, uint32_t &mlo, uint32_t &mhi)
-{
-    mlo = 0u; mhi = 0u;
-#pragma unroll
-    for (int c = 0; c < 8; c++) {
-        const uint4 q = *reinterpret_cast<const uint4 *>(blk + (((c ^ swz) & 7) << 4));
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-        uint32_t m = 0u;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (w[j] & 0xFFFFu) m |= 1u << (2 * j);
-            if (w[j] >> 16) m |= 2u << (2 * j);
+// Packs fields MSB-first into a private column of shared memory: word k of column c lives at
+// col[k * kCols] (word-interleaved, so any mix of k across the lanes of a warp is conflict free).
+struct PrivSink {
+    uint32_t *col;
+    uint32_t acc;                 // pending bits, left aligned
+    int nb;                       // number of pending bits (< 32)
+    int k;                        // words already stored
+    __device__ __forceinline__ void begin(uint32_t *c) { col = c; acc = 0u; nb = 0; k = 0; }
+    __device__ __forceinline__ void put(uint32_t val, int len)      // 1 <= len <= 32, val < 2^len
+    {
+        const uint32_t x = val << (32 - len);                        // left aligned field
+        acc |= x >> nb;
+        const int n = nb + len;
+        if (n >= 32) {
+            col[k * kCols] = acc;
+            k++;
+            acc = nb ? x << (32 - nb) : 0u;
+            nb = n - 32;
+        } else {
+            nb = n;
         }
-        if (c < 4) mlo |= m << (8 * c);
-        else mhi |= m << (8 * (c - 4));
     }
-}
+    __device__ __forceinline__ int bits() const { return k * 32 + nb; }
+    __device__ __forceinline__ void flush() { col[k * kCols] = acc; }   // zero padded partial word
+};
 
-// Sparse walk: only the non-zero AC positions (bits of the mask) are visited.
-template <bool EAGER, class Sink>
-__device__ __forceinline__ void walk_sparse(uint32_t mlo, uint32_t mhi, int diff, const uint8_t *blk, int swz,
-                                            const uint32_t *__restrict__ lut_dc, const uint32_t *__restrict__ lut_ac, Sink &sink)
+// Sparse walk of one block: only the non-zero AC positions (set bits of the mask) are visited.
+// blk: the block's 32 words (two coefficients per word) in shared memory.  With PARTIAL the walk
+// stops once 32 bits are out (lookahead blocks only have to complete the previous word).
+template <bool EAGER, bool PARTIAL>
+__device__ __forceinline__ void encode_block(uint32_t mlo, uint32_t mhi, int diff, const uint32_t *blk,
+                                             const uint32_t *__restrict__ lut_dc, const uint32_t *__restrict__ lut_ac,
+                                             PrivSink &sink)
 {
     {
         const int s = bit_size(diff);
@@ -87,28 +94,35 @@ __device__ __forceinline__ void walk_sparse(uint32_t mlo, uint32_t mhi, int diff
         sink.put(((e & 0xFFFFu) << s) | extra, (int)(e >> 16) + s);
     }
     const uint32_t zrl = lut_ac[0xF0], eob = lut_ac[0x00];
+    const int16_t *c16 = reinterpret_cast<const int16_t *>(blk);
     int prev = 0;
-    uint32_t m = mlo & ~1u;                         // position 0 is the DC
+    uint32_t m = mlo & ~1u;                                         // position 0 is the DC
     int base = 0;
 #pragma unroll 1
     for (int half = 0; half < 2; half++) {
 #pragma unroll 1
         while (m) {
+            if (PARTIAL && sink.k > 0) return;
             const int z = base + __ffs((int)m) - 1;
             m &= m - 1u;
-            const int v = coef_at(blk, swz, z);
+            const int v = (int)c16[z];
             const int run = z - prev - 1;
             prev = z;
-            for (int n = run >> 4; n > 0; n--) sink.put(zrl & 0xFFFFu, (int)(zrl >> 16));   // same for both ZRL policies
+            if (run >= 16) {                                        // ZRLs in front of a non-zero: same for both policies
+#pragma unroll 1
+                for (int n = run >> 4; n > 0; n--) sink.put(zrl & 0xFFFFu, (int)(zrl >> 16));
+            }
             const int s = bit_size(v);
             const uint32_t e = lut_ac[((run & 15) << 4) | s];
-            sink.put(((e & 0xFFFFu) << s) | ((uint32_t)(v < 0 ? v - 1 : v) & ((1u << s) - 1u)), (int)(e >> 16) + s);
+            sink.put(((e & 0xFFFFu) << s) | ((uint32_t)(v + (v >> 31)) & ((1u << s) - 1u)), (int)(e >> 16) + s);
         }
         m = mhi;
         base = 32;
     }
-    const int t = 63 - prev;                        // trailing zeros
-    if (EAGER) {                                    // rlecore.py:101-114
+    if (PARTIAL && sink.k > 0) return;
+    const int t = 63 - prev;                                        // trailing zeros
+    if (EAGER) {                                                    // rlecore.py:101-114
+#pragma unroll 1
         for (int n = t >> 4; n > 0; n--) sink.put(zrl & 0xFFFFu, (int)(zrl >> 16));
         if (t & 15) sink.put(eob & 0xFFFFu, (int)(eob >> 16));
     } else if (t > 0) {
@@ -116,75 +130,62 @@ __device__ __forceinline__ void walk_sparse(uint32_t mlo, uint32_t mhi, int diff
     }
 }
 
-struct CountSink2 {
-    int bits;
-    __device__ __forceinline__ void put(uint32_t, int len) { bits += len; }
-};
-
-// Emits into the shared staging window; words at or beyond `limit` are dropped (lookahead
-// blocks only contribute the bits that complete the chunk's last owned word).
-struct StageSink {
-    uint32_t *stage;
-    unsigned long long acc;
-    int nbits, widx, limit;
-    __device__ __forceinline__ void begin(uint32_t *s, uint32_t bitpos, int lim)
-    {
-        stage = s; acc = 0ull; nbits = (int)(bitpos & 31u); widx = (int)(bitpos >> 5); limit = lim;
-    }
-    __device__ __forceinline__ void put(uint32_t val, int len)
-    {
-        acc = (acc << len) | val;
-        nbits += len;
-        if (nbits >= 32) {
-            if (widx < limit) atomicOr(stage + widx, (uint32_t)(acc >> (nbits - 32)));
-            widx++;
-            nbits -= 32;
-        }
-    }
-    __device__ __forceinline__ void finish()
-    {
-        if (nbits > 0 && widx < limit) atomicOr(stage + widx, (uint32_t)(acc << (32 - nbits)));
-    }
-};
-
 template <bool EAGER>
 __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant__ FusedEntropyParams P,
                                                           const __grid_constant__ LutParam L)
 {
-    __shared__ __align__(16) uint8_t s_coef[(kChunk + kLookahead) * 128];
-    __shared__ uint32_t s_stage[kWinWords + kSlackWords];
-    __shared__ uint32_t s_dc[32], s_ac[512];
-    __shared__ uint32_t s_warp[4];
-    __shared__ unsigned long long s_prefix;
-    __shared__ unsigned int s_id;
-
+    extern __shared__ __align__(16) uint32_t fsm[];
+    uint32_t *s_coef = fsm;                                  // [kCols][kPitch]
+    uint32_t *s_priv = s_coef + kCols * kPitch;              // [kPrivWords][kCols]
+    uint32_t *s_nbits = s_priv + kPrivWords * kCols;         // [kCols]
+    uint32_t *s_mask = s_nbits + kCols;                      // [kCols][2]: eight mask bytes per block
+    uint32_t *s_dc = s_mask + kCols * 2;                     // [2][16]
+    uint32_t *s_ac = s_dc + 32;                              // [2][256]
+    uint32_t *s_misc = s_ac + 512;                           // warp sums [4], ticket, prefix lo/hi
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_id = atomicAdd(P.ticket, 1u);
+    if (tid == 0) s_misc[4] = atomicAdd(P.ticket, 1u);
     load_lut(L, s_dc, s_ac);
     __syncthreads();
-    const unsigned int id = s_id;
-    const int f = (int)(id / (unsigned)P.chunks), ch = (int)(id % (unsigned)P.chunks);
+    const unsigned int id = s_misc[4];
+    // tickets interleave the frames: consecutive CTAs work on different frames, so the predecessor
+    // chunk of the same frame was started n_frames tickets earlier and has usually published its
+    // inclusive prefix by the time it is needed (short look-back, no serial chain inside a wave)
+    const int f = (int)(id % (unsigned)P.e.n_frames), ch = (int)(id / (unsigned)P.e.n_frames);
     const EGeo &e = P.e;
     const long long b0 = (long long)ch * kChunk;
     const long long b1 = min(b0 + kChunk, e.nblk);
     const long long bl = min(b1 + kLookahead, e.nblk);              // end of the lookahead blocks
+    const int nown = (int)(b1 - b0), nall = (int)(bl - b0);
     const int16_t *fc = P.coefs + (long long)f * e.nblk * 64;
     const bool last = b1 >= e.nblk;
 
-    // ---- 1. coalesced load of the chunk (+ lookahead) into swizzled shared memory
+    // ---- 1. coalesced load (16-byte pieces) into the padded layout + non-zero byte masks
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(fc + b0 * 64);
-        const int npieces = (int)(bl - b0) * 8;
+        uint8_t *mask8 = reinterpret_cast<uint8_t *>(s_mask);
+        const int npieces = nall * 8;
         for (int i = tid; i < npieces; i += kChunk) {
             const int b = i >> 3, c = i & 7;
-            *reinterpret_cast<uint4 *>(s_coef + b * 128 + (((c ^ b) & 7) << 4)) = __ldg(src + i);
+            const uint4 q = __ldg(src + i);
+            uint32_t *d = s_coef + b * kPitch + c * 4;
+            d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
+            uint32_t m = 0u;
+            if (q.x & 0xFFFFu) m |= 1u;
+            if (q.x >> 16) m |= 2u;
+            if (q.y & 0xFFFFu) m |= 4u;
+            if (q.y >> 16) m |= 8u;
+            if (q.z & 0xFFFFu) m |= 16u;
+            if (q.z >> 16) m |= 32u;
+            if (q.w & 0xFFFFu) m |= 64u;
+            if (q.w >> 16) m |= 128u;
+            mask8[b * 8 + c] = (uint8_t)m;
         }
     }
     __syncthreads();
 
-    // ---- 2. per block: mask, DC difference, bit count
+    // ---- 2. one walk per block: private packed bits + bit count
     auto dc_of = [&](long long b) -> int {          // DC of block b of this frame (b < bl)
-        if (b >= b0) return coef_at(s_coef + (int)(b - b0) * 128, (int)(b - b0) & 7, 0);
+        if (b >= b0) return (int)(int16_t)(s_coef[(int)(b - b0) * kPitch] & 0xFFFFu);
         return b >= 0 ? (int)fc[b * 64] : 0;
     };
     auto prev_index = [&](long long b) -> long long {
@@ -192,28 +193,41 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
         if (k < e.hv) return k > 0 ? b - 1 : b - e.bpm + e.hv - 1;
         return b - e.bpm;
     };
-    const long long myb = b0 + tid;
-    const bool own = myb < b1;
-    uint32_t mlo = 0u, mhi = 0u;
-    int diff = 0, chroma = 0, mybits = 0;
-    const uint8_t *myblk = s_coef + tid * 128;
-    if (own) {
-        block_mask(myblk, tid & 7, mlo, mhi);
-        chroma = (int)(myb % e.bpm) >= e.hv;
-        diff = coef_at(myblk, tid & 7, 0) - dc_of(prev_index(myb));
-        CountSink2 cs{0};
-        walk_sparse<EAGER>(mlo, mhi, diff, myblk, tid & 7, s_dc + 16 * chroma, s_ac + 256 * chroma, cs);
-        mybits = cs.bits;
+    PrivSink sink;
+    sink.begin(s_priv + tid);
+    int mybits = 0;
+    if (tid < nown) {
+        const long long b = b0 + tid;
+        const uint32_t *blk = s_coef + tid * kPitch;
+        const int chroma = (int)(b % e.bpm) >= e.hv;
+        const int diff = (int)(int16_t)(blk[0] & 0xFFFFu) - dc_of(prev_index(b));
+        encode_block<EAGER, false>(s_mask[tid * 2], s_mask[tid * 2 + 1], diff, blk, s_dc + 16 * chroma, s_ac + 256 * chroma, sink);
+        sink.flush();
+        mybits = sink.bits();
+        s_nbits[tid] = (uint32_t)mybits;
+    }
+    // the lookahead blocks only have to supply the bits that complete this chunk's last word
+    if (tid < kLookahead && kChunk + tid < nall && !last) {
+        const int colidx = kChunk + tid;
+        const long long b = b0 + colidx;
+        const uint32_t *blk = s_coef + colidx * kPitch;
+        const int chroma = (int)(b % e.bpm) >= e.hv;
+        const int diff = (int)(int16_t)(blk[0] & 0xFFFFu) - dc_of(prev_index(b));
+        PrivSink sk;
+        sk.begin(s_priv + colidx);
+        encode_block<EAGER, true>(s_mask[colidx * 2], s_mask[colidx * 2 + 1], diff, blk, s_dc + 16 * chroma, s_ac + 256 * chroma, sk);
+        sk.flush();
+        s_nbits[colidx] = (uint32_t)sk.bits();                      // >= 32 when the walk was cut short
     }
 
     // ---- 3. CTA exclusive scan of the bit counts
-    uint32_t inc = warp_incl_scan((uint32_t)mybits);
-    if (lane == 31) s_warp[warp] = inc;
+    const uint32_t inc = warp_incl_scan((uint32_t)mybits);
+    if (lane == 31) s_misc[warp] = inc;
     __syncthreads();
     uint32_t wbase_bits = 0, T = 0;
 #pragma unroll
     for (int w = 0; w < 4; w++) {
-        const uint32_t x = s_warp[w];
+        const uint32_t x = s_misc[w];
         if (w < warp) wbase_bits += x;
         T += x;
     }
@@ -248,86 +262,45 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
         }
         if (lane == 0) {
             st_volatile(st + ch, kFlagP | (E + (unsigned long long)T));
-            s_prefix = E;
+            s_misc[5] = (uint32_t)E;
+            s_misc[6] = (uint32_t)(E >> 32);
         }
     }
     __syncthreads();
-    const unsigned long long E = s_prefix;                           // bits of the frame before this chunk
+    const unsigned long long E = (unsigned long long)s_misc[5] | ((unsigned long long)s_misc[6] << 32);
 
-    // ---- 4. emit.  Global bit g of the frame lives in word g >> 5 of the frame's stream.
-    const unsigned long long Eend = E + T;
-    const unsigned long long Epad = last ? ((Eend + 7ull) & ~7ull) : Eend;
-    const unsigned long long W0 = (E + 31ull) >> 5, W1 = (Epad + 31ull) >> 5;     // owned words [W0, W1)
-    const unsigned long long B0 = (E >> 5) << 5;                                   // window origin (bit)
-    const unsigned long long myG = E + excl;                                       // first bit of my block
-    constexpr unsigned long long WB = (unsigned long long)kWinWords * 32ull;
-    const int n_rounds = (int)((Epad - B0 + WB - 1ull) / WB) > 0 ? (int)((Epad - B0 + WB - 1ull) / WB) : 1;
-    uint32_t *dst = reinterpret_cast<uint32_t *>(P.unstuffed + (long long)f * P.ucap);
-    const unsigned long long wcap = (unsigned long long)(P.ucap >> 2);
-
-    for (int r = 0; r < n_rounds; r++) {
-        const unsigned long long wb = B0 + (unsigned long long)r * WB;            // first bit of this window
-        if (r == 0) {
-            for (int i = tid; i < kWinWords + kSlackWords; i += kChunk) s_stage[i] = 0u;
-        } else {
-            // bits that spilled past the previous window are the first words of this one
-            __syncthreads();
-            const uint32_t carry = tid < kSlackWords ? s_stage[kWinWords + tid] : 0u;
-            __syncthreads();
-            for (int i = tid; i < kWinWords + kSlackWords; i += kChunk) s_stage[i] = 0u;
-            __syncthreads();
-            if (tid < kSlackWords) s_stage[tid] = carry;
-        }
-        __syncthreads();
-        const bool final_round = r == n_rounds - 1;
-        if (own && myG >= wb && myG < wb + WB) {
-            StageSink sink;
-            sink.begin(s_stage, (uint32_t)(myG - wb), kWinWords + kSlackWords);
-            walk_sparse<EAGER>(mlo, mhi, diff, myblk, tid & 7, s_dc + 16 * chroma, s_ac + 256 * chroma, sink);
-            sink.finish();
-        }
-        if (final_round) {
-            // lookahead: the first bits of the following blocks complete the last owned word
-            const unsigned long long lim_bit = W1 << 5;
-            if (!last && warp == 0) {
-                // bit offsets of the lookahead blocks: serial prefix over at most 8 counts
-                const long long lb = b1 + lane;
-                const bool act = lane < kLookahead && lb < bl;
-                uint32_t lmlo = 0u, lmhi = 0u;
-                int ldiff = 0, lchroma = 0, lbits = 0;
-                const uint8_t *lblk = s_coef + (int)(lb - b0) * 128;
-                const int lswz = (int)(lb - b0) & 7;
-                if (act) {
-                    block_mask(lblk, lswz, lmlo, lmhi);
-                    lchroma = (int)(lb % e.bpm) >= e.hv;
-                    ldiff = coef_at(lblk, lswz, 0) - dc_of(prev_index(lb));
-                    CountSink2 cs{0};
-                    walk_sparse<EAGER>(lmlo, lmhi, ldiff, lblk, lswz, s_dc + 16 * lchroma, s_ac + 256 * lchroma, cs);
-                    lbits = cs.bits;
-                }
-                const uint32_t linc = warp_incl_scan((uint32_t)lbits);
-                const unsigned long long lG = Eend + (linc - (uint32_t)lbits);
-                if (act && lG < lim_bit) {
-                    StageSink sink;
-                    sink.begin(s_stage, (uint32_t)(lG - wb), (int)((lim_bit - wb) >> 5));
-                    walk_sparse<EAGER>(lmlo, lmhi, ldiff, lblk, lswz, s_dc + 16 * lchroma, s_ac + 256 * lchroma, sink);
-                    sink.finish();
-                }
+    // ---- 4. compose the owned words.  Bit g of the frame's stream lives in word g >> 5.
+    if (tid < nown) {
+        const unsigned long long G = E + excl;
+        unsigned long long Gn = G + (unsigned)mybits;
+        if (last && tid == nown - 1) {                               // pad the final byte of the frame with 1s
+            const int pad = (int)((8ull - (Gn & 7ull)) & 7ull);
+            if (pad) {
+                sink.put((1u << pad) - 1u, pad);
+                sink.flush();
+                Gn += (unsigned)pad;
             }
-            if (last && tid == 0 && Epad > Eend) {                   // pad the final byte with 1s
-                const uint32_t pos = (uint32_t)(Eend - wb), n = (uint32_t)(Epad - Eend);
-                atomicOr(s_stage + (pos >> 5), ((1u << n) - 1u) << (32u - (pos & 31u) - n));
-            }
+            P.total_bits[f] = (int64_t)(G + (unsigned)mybits);
         }
-        __syncthreads();
-        // store the owned words that are complete in this window (big-endian bytes)
-        const unsigned long long wlo = wb >> 5;
-        const unsigned long long whi = final_round ? W1 : wlo + kWinWords;
-        const unsigned long long lo = W0 > wlo ? W0 : wlo, hi = W1 < whi ? W1 : whi;
-        for (unsigned long long w = lo + tid; w < hi; w += kChunk)
-            if (w < wcap) dst[w] = __byte_perm(s_stage[(int)(w - wlo)], 0u, 0x0123);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(P.unstuffed + (long long)f * P.ucap);
+        const unsigned long long wcap = (unsigned long long)(P.ucap >> 2);
+        const uint32_t *mine = s_priv + tid;
+        const int total = (int)(Gn - G);
+        for (unsigned long long w = (G + 31ull) >> 5; w < ((Gn + 31ull) >> 5); w++) {
+            const int rel = (int)((w << 5) - G);                     // first bit of this word inside my block
+            const int k = rel >> 5, sh = rel & 31;
+            const uint32_t a = mine[k * kCols];
+            const uint32_t bnext = (k + 1) * 32 < total ? mine[(k + 1) * kCols] : 0u;
+            uint32_t v = __funnelshift_l(bnext, a, sh);
+            int have = total - rel;                                  // my bits available from `rel`
+            // complete the word with the first bits of the following blocks
+            for (int nb = tid + 1; have < 32 && nb < nall && !(last && nb >= nown); nb++) {
+                v |= s_priv[nb] >> have;
+                have += (int)s_nbits[nb];
+            }
+            if (w < wcap) dst[w] = __byte_perm(v, 0u, 0x0123);      // big-endian bytes
+        }
     }
-    if (last && tid == 0) P.total_bits[f] = (int64_t)Eend;
 }
 
 }  // namespace b2j
@@ -394,8 +367,13 @@ extern "C" int b2j_entropy_encode(const int16_t *coefs, const b2j_image_desc *de
     cudaStream_t st = as_stream(stream);
     B2J_CUDA(cudaMemsetAsync(ws, 0, status_bytes, st));              // ticket, error flag, chunk status words
     const unsigned grid = (unsigned)((long long)chunks * g.n_frames);
-    if (zrl == B2J_ZRL_EAGER) k_entropy_fused<true><<<grid, kChunk, 0, st>>>(P, L);
-    else k_entropy_fused<false><<<grid, kChunk, 0, st>>>(P, L);
+    if (zrl == B2J_ZRL_EAGER) {
+        B2J_CUDA(cudaFuncSetAttribute(k_entropy_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem));
+        k_entropy_fused<true><<<grid, kChunk, kFusedSmem, st>>>(P, L);
+    } else {
+        B2J_CUDA(cudaFuncSetAttribute(k_entropy_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem));
+        k_entropy_fused<false><<<grid, kChunk, kFusedSmem, st>>>(P, L);
+    }
     B2J_LAUNCH_CHECK("k_entropy_fused");
     return launch_stuffing(P.unstuffed, P.total_bits, ffpart, sizes, out, ucap, out_cap, g.n_frames, H, P.error_flag, st);
 }
