@@ -26,9 +26,13 @@ constexpr int kLookahead = 8;                     // >= 31 bits / (4 bits per sm
 constexpr int kCols = kChunk + kLookahead;        // blocks held in shared memory
 constexpr int kPitch = 33;                        // words per block in shared memory (32 + 1 pad)
 constexpr int kPrivWords = 55;                    // >= (1728 + 7 pad bits) / 32 + 1
+constexpr int kCap = 8;                           // private words kept in shared memory (256 bits); the rest of a
+                                                  // (rare) larger block goes to an L2-resident scratch column
+constexpr int kOvfWords = kPrivWords - kCap;
+constexpr int kMaxSlots = 2048;                   // persistent CTAs that may own a scratch slot
 constexpr unsigned long long kFlagA = 1ull << 62, kFlagP = 2ull << 62, kValMask = (1ull << 62) - 1;
 constexpr int kSpinLimit = 1 << 22;
-constexpr int kFusedSmem = (kCols * kPitch + kPrivWords * kCols + kCols + kCols * 2 + 32 + 512 + 16) * 4;
+constexpr int kFusedSmem = (kCols * kPitch + kCap * kCols + kCols + kCols * 2 + 32 + 512 + 16) * 4;
 
 struct FusedEntropyParams {
     const int16_t *coefs;
@@ -37,6 +41,7 @@ struct FusedEntropyParams {
     unsigned long long *status;   // [n_frames * chunks]
     unsigned int *ticket;
     int *error_flag;
+    uint32_t *overflow;           // [gridDim.x][kOvfWords][kCols]
     long long ucap;
     int chunks;
     EGeo e;
@@ -56,18 +61,25 @@ __device__ __forceinline__ void st_volatile(unsigned long long *p, unsigned long
 // Packs fields MSB-first into a private column of shared memory: word k of column c lives at
 // col[k * kCols] (word-interleaved, so any mix of k across the lanes of a warp is conflict free).
 struct PrivSink {
-    uint32_t *col;
+    uint32_t *col;                // shared column (first kCap words)
+    uint32_t *ovf;                // global scratch column (words kCap..)
     uint32_t acc;                 // pending bits, left aligned
     int nb;                       // number of pending bits (< 32)
     int k;                        // words already stored
-    __device__ __forceinline__ void begin(uint32_t *c) { col = c; acc = 0u; nb = 0; k = 0; }
+    __device__ __forceinline__ void begin(uint32_t *c, uint32_t *o) { col = c; ovf = o; acc = 0u; nb = 0; k = 0; }
+    __device__ __forceinline__ void store(uint32_t w)
+    {
+        if (k < kCap) col[k * kCols] = w;
+        else ovf[(k - kCap) * kCols] = w;
+    }
+    __device__ __forceinline__ uint32_t load(int i) const { return i < kCap ? col[i * kCols] : ovf[(i - kCap) * kCols]; }
     __device__ __forceinline__ void put(uint32_t val, int len)      // 1 <= len <= 32, val < 2^len
     {
         const uint32_t x = val << (32 - len);                        // left aligned field
         acc |= x >> nb;
         const int n = nb + len;
         if (n >= 32) {
-            col[k * kCols] = acc;
+            store(acc);
             k++;
             acc = nb ? x << (32 - nb) : 0u;
             nb = n - 32;
@@ -76,7 +88,7 @@ struct PrivSink {
         }
     }
     __device__ __forceinline__ int bits() const { return k * 32 + nb; }
-    __device__ __forceinline__ void flush() { col[k * kCols] = acc; }   // zero padded partial word
+    __device__ __forceinline__ void flush() { store(acc); }         // zero padded partial word
 };
 
 // Sparse walk of one block: only the non-zero AC positions (set bits of the mask) are visited.
@@ -136,17 +148,22 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
 {
     extern __shared__ __align__(16) uint32_t fsm[];
     uint32_t *s_coef = fsm;                                  // [kCols][kPitch]
-    uint32_t *s_priv = s_coef + kCols * kPitch;              // [kPrivWords][kCols]
-    uint32_t *s_nbits = s_priv + kPrivWords * kCols;         // [kCols]
+    uint32_t *s_priv = s_coef + kCols * kPitch;              // [kCap][kCols]
+    uint32_t *s_nbits = s_priv + kCap * kCols;               // [kCols]
     uint32_t *s_mask = s_nbits + kCols;                      // [kCols][2]: eight mask bytes per block
     uint32_t *s_dc = s_mask + kCols * 2;                     // [2][16]
     uint32_t *s_ac = s_dc + 32;                              // [2][256]
     uint32_t *s_misc = s_ac + 512;                           // warp sums [4], ticket, prefix lo/hi
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_misc[4] = atomicAdd(P.ticket, 1u);
+    uint32_t *my_ovf = P.overflow + (size_t)blockIdx.x * kOvfWords * kCols;
+    const unsigned int total_chunks = (unsigned)P.chunks * (unsigned)P.e.n_frames;
     load_lut(L, s_dc, s_ac);
+  for (;;) {                                                          // persistent: one chunk per ticket
+    __syncthreads();                                                  // shared memory of the previous chunk is free
+    if (tid == 0) s_misc[4] = atomicAdd(P.ticket, 1u);
     __syncthreads();
     const unsigned int id = s_misc[4];
+    if (id >= total_chunks) break;
     // tickets interleave the frames: consecutive CTAs work on different frames, so the predecessor
     // chunk of the same frame was started n_frames tickets earlier and has usually published its
     // inclusive prefix by the time it is needed (short look-back, no serial chain inside a wave)
@@ -194,7 +211,7 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
         return b - e.bpm;
     };
     PrivSink sink;
-    sink.begin(s_priv + tid);
+    sink.begin(s_priv + tid, my_ovf + tid);
     int mybits = 0;
     if (tid < nown) {
         const long long b = b0 + tid;
@@ -214,7 +231,7 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
         const int chroma = (int)(b % e.bpm) >= e.hv;
         const int diff = (int)(int16_t)(blk[0] & 0xFFFFu) - dc_of(prev_index(b));
         PrivSink sk;
-        sk.begin(s_priv + colidx);
+        sk.begin(s_priv + colidx, nullptr);
         encode_block<EAGER, true>(s_mask[colidx * 2], s_mask[colidx * 2 + 1], diff, blk, s_dc + 16 * chroma, s_ac + 256 * chroma, sk);
         sk.flush();
         s_nbits[colidx] = (uint32_t)sk.bits();                      // >= 32 when the walk was cut short
@@ -284,13 +301,12 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
         }
         uint32_t *dst = reinterpret_cast<uint32_t *>(P.unstuffed + (long long)f * P.ucap);
         const unsigned long long wcap = (unsigned long long)(P.ucap >> 2);
-        const uint32_t *mine = s_priv + tid;
         const int total = (int)(Gn - G);
         for (unsigned long long w = (G + 31ull) >> 5; w < ((Gn + 31ull) >> 5); w++) {
             const int rel = (int)((w << 5) - G);                     // first bit of this word inside my block
             const int k = rel >> 5, sh = rel & 31;
-            const uint32_t a = mine[k * kCols];
-            const uint32_t bnext = (k + 1) * 32 < total ? mine[(k + 1) * kCols] : 0u;
+            const uint32_t a = sink.load(k);
+            const uint32_t bnext = (k + 1) * 32 < total ? sink.load(k + 1) : 0u;
             uint32_t v = __funnelshift_l(bnext, a, sh);
             int have = total - rel;                                  // my bits available from `rel`
             // complete the word with the first bits of the following blocks
@@ -301,6 +317,7 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
             if (w < wcap) dst[w] = __byte_perm(v, 0u, 0x0123);      // big-endian bytes
         }
     }
+  }
 }
 
 }  // namespace b2j
@@ -321,7 +338,8 @@ extern "C" size_t b2j_entropy_workspace_bytes(const b2j_image_desc *desc, int64_
     size_t o = (fused_status_bytes(g) + 255) & ~(size_t)255;
     o += ((size_t)g.n_frames * sizeof(int64_t) + 255) & ~(size_t)255;
     o += (size_t)g.n_frames * (size_t)ucap;
-    o += (size_t)g.n_frames * stuff_chunks(ucap) * sizeof(uint32_t) + 512;
+    o += ((size_t)g.n_frames * stuff_chunks(ucap) * sizeof(uint32_t) + 511) & ~(size_t)255;
+    o += (size_t)kMaxSlots * kOvfWords * kCols * sizeof(uint32_t);
     return o;
 }
 
@@ -354,6 +372,8 @@ extern "C" int b2j_entropy_encode(const int16_t *coefs, const b2j_image_desc *de
     P.unstuffed = ws + o;
     o += (size_t)g.n_frames * (size_t)ucap;
     uint32_t *ffpart = reinterpret_cast<uint32_t *>(ws + o);
+    o += ((size_t)g.n_frames * stuff_chunks(ucap) * sizeof(uint32_t) + 511) & ~(size_t)255;
+    P.overflow = reinterpret_cast<uint32_t *>(ws + o);
     P.ucap = ucap;
     P.chunks = chunks;
     P.e = egeo_of(g);
@@ -366,14 +386,22 @@ extern "C" int b2j_entropy_encode(const int16_t *coefs, const b2j_image_desc *de
     const LutParam L = make_lut_param();
     cudaStream_t st = as_stream(stream);
     B2J_CUDA(cudaMemsetAsync(ws, 0, status_bytes, st));              // ticket, error flag, chunk status words
-    const unsigned grid = (unsigned)((long long)chunks * g.n_frames);
+    const long long total = (long long)chunks * g.n_frames;
+    int dev = 0, sms = 148, per_sm = 1;
+    B2J_CUDA(cudaGetDevice(&dev));
+    B2J_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (zrl == B2J_ZRL_EAGER) {
         B2J_CUDA(cudaFuncSetAttribute(k_entropy_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem));
-        k_entropy_fused<true><<<grid, kChunk, kFusedSmem, st>>>(P, L);
+        B2J_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_entropy_fused<true>, kChunk, kFusedSmem));
     } else {
         B2J_CUDA(cudaFuncSetAttribute(k_entropy_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem));
-        k_entropy_fused<false><<<grid, kChunk, kFusedSmem, st>>>(P, L);
+        B2J_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_entropy_fused<false>, kChunk, kFusedSmem));
     }
+    long long slots = (long long)sms * (per_sm < 1 ? 1 : per_sm);
+    if (slots > kMaxSlots) slots = kMaxSlots;
+    const unsigned grid = (unsigned)(total < slots ? total : slots);   // persistent CTAs, one scratch slot each
+    if (zrl == B2J_ZRL_EAGER) k_entropy_fused<true><<<grid, kChunk, kFusedSmem, st>>>(P, L);
+    else k_entropy_fused<false><<<grid, kChunk, kFusedSmem, st>>>(P, L);
     B2J_LAUNCH_CHECK("k_entropy_fused");
     return launch_stuffing(P.unstuffed, P.total_bits, ffpart, sizes, out, ucap, out_cap, g.n_frames, H, P.error_flag, st);
 }
