@@ -351,35 +351,92 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused_tiled(const __grid_consta
         }
 
         // ---------------- phase A: colour conversion + subsampling into 8-bit planes.
-        // work item = 4 consecutive pixels of one row (4:2:0: of a pair of rows); 8 x 256 items per tile
+        // work item = 4 consecutive pixels of one row (4:2:0: of a pair of rows); 8 x 256 items per tile.
+        // The fast path is straight-line integer code for all pixels of the item (no branches, so
+        // the pixels interleave); the rare inputs where the float64 model differs from the exact
+        // rational value are only flagged here and patched afterwards from the raw bytes.
 #pragma unroll 1
         for (int item = tid; item < 8 * (kTileW / 4); item += kThreads) {
             const int ry = item / (kTileW / 4), grp = item % (kTileW / 4);
             if (grp * 4 >= cur.need_px) continue;
-            Ycc A[4], B[4];
-            convert4(raw + (ry * V) * kRawPitch + grp * 12, A, s_crx);
-            *reinterpret_cast<uint32_t *>(s_y + (ry * V) * kTileW + grp * 4) =
-                A[0].y | (A[1].y << 8) | (A[2].y << 16) | (A[3].y << 24);
-            if (V == 2) {
-                convert4(raw + (ry * 2 + 1) * kRawPitch + grp * 12, B, s_crx);
-                *reinterpret_cast<uint32_t *>(s_y + (ry * 2 + 1) * kTileW + grp * 4) =
-                    B[0].y | (B[1].y << 8) | (B[2].y << 16) | (B[3].y << 24);
+            uint32_t sy[V][4], scb[V][4], scr[V][4];
+            bool y_clean = true;
+            uint32_t cr_flag = 0u;
+#pragma unroll
+            for (int v = 0; v < V; v++) {
+                const uint32_t *q = reinterpret_cast<const uint32_t *>(raw + (ry * V + v) * kRawPitch + grp * 12);
+                const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+                uint32_t r[4], g[4], b[4];
+                r[0] = __byte_perm(w0, 0u, 0x4440); g[0] = __byte_perm(w0, 0u, 0x4441); b[0] = __byte_perm(w0, 0u, 0x4442);
+                r[1] = __byte_perm(w0, 0u, 0x4443); g[1] = __byte_perm(w1, 0u, 0x4440); b[1] = __byte_perm(w1, 0u, 0x4441);
+                r[2] = __byte_perm(w1, 0u, 0x4442); g[2] = __byte_perm(w1, 0u, 0x4443); b[2] = __byte_perm(w2, 0u, 0x4440);
+                r[3] = __byte_perm(w2, 0u, 0x4441); g[3] = __byte_perm(w2, 0u, 0x4442); b[3] = __byte_perm(w2, 0u, 0x4443);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    sy[v][i] = csc_sum_y(r[i], g[i], b[i]);
+                    scb[v][i] = csc_sum_cb(r[i], g[i], b[i]);
+                    scr[v][i] = csc_sum_cr(r[i], g[i], b[i]);
+                    y_clean = y_clean && (sy[v][i] & B2J_CONST_EXC_MASK) != 0u;
+                    // Cr candidates (g == b, r - g even) are common; only eight grey levels can differ
+                    cr_flag |= (scr[v][i] & B2J_CONST_EXC_MASK) == 0u ? (uint32_t)s_crx[g[i]] : 0u;
+                }
+            }
+            // luma: the component is the top byte of the sum
+#pragma unroll
+            for (int v = 0; v < V; v++) {
+                const uint32_t lo = __byte_perm(sy[v][0], sy[v][1], 0x0073), hi = __byte_perm(sy[v][2], sy[v][3], 0x0073);
+                *reinterpret_cast<uint32_t *>(s_y + (ry * V + v) * kTileW + grp * 4) = __byte_perm(lo, hi, 0x5410);
             }
             if (H == 1) {
-                *reinterpret_cast<uint32_t *>(s_cb + ry * TS::kCW + grp * 4) =
-                    A[0].cb | (A[1].cb << 8) | (A[2].cb << 16) | (A[3].cb << 24);
-                *reinterpret_cast<uint32_t *>(s_cr + ry * TS::kCW + grp * 4) =
-                    A[0].cr | (A[1].cr << 8) | (A[2].cr << 16) | (A[3].cr << 24);
+                const uint32_t lo = __byte_perm(scb[0][0], scb[0][1], 0x0073), hi = __byte_perm(scb[0][2], scb[0][3], 0x0073);
+                *reinterpret_cast<uint32_t *>(s_cb + ry * TS::kCW + grp * 4) = __byte_perm(lo, hi, 0x5410);
+                const uint32_t lo2 = __byte_perm(scr[0][0], scr[0][1], 0x0073), hi2 = __byte_perm(scr[0][2], scr[0][3], 0x0073);
+                *reinterpret_cast<uint32_t *>(s_cr + ry * TS::kCW + grp * 4) = __byte_perm(lo2, hi2, 0x5410);
             } else {
                 // pair mean (c0 + c1) >> 1 horizontally (crs.py:39-54), then vertically
-                uint32_t cb0 = (A[0].cb + A[1].cb) >> 1, cb1 = (A[2].cb + A[3].cb) >> 1;
-                uint32_t cr0 = (A[0].cr + A[1].cr) >> 1, cr1 = (A[2].cr + A[3].cr) >> 1;
+                uint32_t cb0 = ((scb[0][0] >> 24) + (scb[0][1] >> 24)) >> 1, cb1 = ((scb[0][2] >> 24) + (scb[0][3] >> 24)) >> 1;
+                uint32_t cr0 = ((scr[0][0] >> 24) + (scr[0][1] >> 24)) >> 1, cr1 = ((scr[0][2] >> 24) + (scr[0][3] >> 24)) >> 1;
                 if (V == 2) {
-                    cb0 = (cb0 + ((B[0].cb + B[1].cb) >> 1)) >> 1; cb1 = (cb1 + ((B[2].cb + B[3].cb) >> 1)) >> 1;
-                    cr0 = (cr0 + ((B[0].cr + B[1].cr) >> 1)) >> 1; cr1 = (cr1 + ((B[2].cr + B[3].cr) >> 1)) >> 1;
+                    cb0 = (cb0 + (((scb[V - 1][0] >> 24) + (scb[V - 1][1] >> 24)) >> 1)) >> 1;
+                    cb1 = (cb1 + (((scb[V - 1][2] >> 24) + (scb[V - 1][3] >> 24)) >> 1)) >> 1;
+                    cr0 = (cr0 + (((scr[V - 1][0] >> 24) + (scr[V - 1][1] >> 24)) >> 1)) >> 1;
+                    cr1 = (cr1 + (((scr[V - 1][2] >> 24) + (scr[V - 1][3] >> 24)) >> 1)) >> 1;
                 }
                 *reinterpret_cast<uint16_t *>(s_cb + ry * TS::kCW + grp * 2) = (uint16_t)(cb0 | (cb1 << 8));
                 *reinterpret_cast<uint16_t *>(s_cr + ry * TS::kCW + grp * 2) = (uint16_t)(cr0 | (cr1 << 8));
+            }
+            // ---- rare patch-ups, from the raw bytes (rolled loops: this code must stay small)
+            if (!y_clean) {
+#pragma unroll 1
+                for (int j = 0; j < 4 * V; j++) {
+                    const int v = j >> 2, i = j & 3;
+                    const uint8_t *px = raw + (ry * V + v) * kRawPitch + grp * 12 + i * 3;
+                    const uint32_t r = px[0], g = px[1], b = px[2];
+                    if ((csc_sum_y(r, g, b) & B2J_CONST_EXC_MASK) == 0u)
+                        s_y[(ry * V + v) * kTileW + grp * 4 + i] = (uint8_t)csc_y_fp64(r, g, b);
+                }
+            }
+            if (cr_flag != 0u) {
+                constexpr int kSamples = 4 / H;                  // chroma samples of this item
+#pragma unroll 1
+                for (int c = 0; c < kSamples; c++) {
+                    uint32_t acc_v = 0u;
+#pragma unroll 1
+                    for (int v = 0; v < V; v++) {
+                        uint32_t acc_h = 0u;
+#pragma unroll 1
+                        for (int h = 0; h < H; h++) {
+                            const uint8_t *px = raw + (ry * V + v) * kRawPitch + grp * 12 + (c * H + h) * 3;
+                            const uint32_t r = px[0], g = px[1], b = px[2];
+                            const uint32_t sc = csc_sum_cr(r, g, b);
+                            uint32_t cr = sc >> 24;
+                            if ((sc & B2J_CONST_EXC_MASK) == 0u) cr -= cr_exception(r, g);
+                            acc_h += cr;
+                        }
+                        acc_v += H == 2 ? acc_h >> 1 : acc_h;
+                    }
+                    s_cr[ry * TS::kCW + grp * kSamples + c] = (uint8_t)(V == 2 ? acc_v >> 1 : acc_v);
+                }
             }
         }
         __syncthreads();        // planes complete; raw buffer is free again

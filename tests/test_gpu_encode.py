@@ -99,6 +99,35 @@ def test_full_encode_bytes_equal_oracle(lj, oracle_c, sub, kind):
             assert f == oracle_c.encode_jpeg(frames[i].numpy(), sub, q, 0 if zrl == "eager" else 1), (q, zrl, i)
 
 
+def test_colour_exception_inputs_through_the_fused_kernel(lj, oracle_c):
+    """Every input where the float64 colour model differs from the exact rational value (3464 for
+    Y, 688 for Cr) plus look-alike candidates, laid out as an image: the fused kernel's patch-up
+    path must reproduce the model for all of them, in every subsampling mode."""
+    allv = np.arange(1 << 24, dtype=np.int64)
+    R, G, B = allv >> 16, (allv >> 8) & 255, allv & 255
+    Y, CB, CR = M.rgb2ycbcr(R, G, B)
+    ny = 299 * R + 587 * G + 114 * B
+    ncr = 5000 * R - 4187 * G - 813 * B + 1280000
+    sel = np.nonzero((ny % 1000 == 0) | ((ncr % 10000 == 0) & (G >= 150)))[0]
+    assert (Y[sel] != ny[sel] // 1000).sum() == 3464 and (CR[sel] != ncr[sel] // 10000).sum() == 688
+    rng = np.random.default_rng(11)
+    sel = np.concatenate([sel, sel[rng.permutation(sel.size)[:4096]]])        # some twice, in another order
+    w = 256
+    h = (sel.size + w - 1) // w
+    h += (-h) % 16
+    img = np.zeros((h * w, 3), np.uint8)
+    img[:sel.size, 0], img[:sel.size, 1], img[:sel.size, 2] = R[sel], G[sel], B[sel]
+    img[sel.size:] = img[:h * w - sel.size]
+    img = img.reshape(h, w, 3)
+    qy, qc = J.quant_tables(100)                                              # divisors 1: nothing is hidden by rounding
+    for sub in SUBS:
+        enc = lj.JpegEncoder(sub, quality=100)
+        exp = oracle_c.coefficients(img, sub, qy, qc).reshape(-1, 64)
+        for variant in ("tiled", "simple"):
+            got = enc.coefficients(torch.from_numpy(img).cuda(), variant=variant).cpu().numpy()[0]
+            assert np.array_equal(got, exp), (sub, variant)
+
+
 def test_lena_files_decode(lj, oracle_c, golden):
     """The emitted files open in PIL / OpenCV and the oracle decoder recovers the model's coefficients."""
     from PIL import Image
