@@ -405,37 +405,39 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused_tiled(const __grid_consta
                 *reinterpret_cast<uint16_t *>(s_cb + ry * TS::kCW + grp * 2) = (uint16_t)(cb0 | (cb1 << 8));
                 *reinterpret_cast<uint16_t *>(s_cr + ry * TS::kCW + grp * 2) = (uint16_t)(cr0 | (cr1 << 8));
             }
-            // ---- rare patch-ups, from the raw bytes (rolled loops: this code must stay small)
+            // ---- rare patch-ups: the sums are still in registers, r/g/b are re-read from the raw bytes
             if (!y_clean) {
-#pragma unroll 1
-                for (int j = 0; j < 4 * V; j++) {
-                    const int v = j >> 2, i = j & 3;
-                    const uint8_t *px = raw + (ry * V + v) * kRawPitch + grp * 12 + i * 3;
-                    const uint32_t r = px[0], g = px[1], b = px[2];
-                    if ((csc_sum_y(r, g, b) & B2J_CONST_EXC_MASK) == 0u)
-                        s_y[(ry * V + v) * kTileW + grp * 4 + i] = (uint8_t)csc_y_fp64(r, g, b);
-                }
+#pragma unroll
+                for (int v = 0; v < V; v++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        if ((sy[v][i] & B2J_CONST_EXC_MASK) == 0u) {
+                            const uint8_t *px = raw + (ry * V + v) * kRawPitch + grp * 12 + i * 3;
+                            s_y[(ry * V + v) * kTileW + grp * 4 + i] = (uint8_t)csc_y_fp64(px[0], px[1], px[2]);
+                        }
             }
             if (cr_flag != 0u) {
-                constexpr int kSamples = 4 / H;                  // chroma samples of this item
-#pragma unroll 1
-                for (int c = 0; c < kSamples; c++) {
-                    uint32_t acc_v = 0u;
-#pragma unroll 1
-                    for (int v = 0; v < V; v++) {
-                        uint32_t acc_h = 0u;
-#pragma unroll 1
-                        for (int h = 0; h < H; h++) {
-                            const uint8_t *px = raw + (ry * V + v) * kRawPitch + grp * 12 + (c * H + h) * 3;
-                            const uint32_t r = px[0], g = px[1], b = px[2];
-                            const uint32_t sc = csc_sum_cr(r, g, b);
-                            uint32_t cr = sc >> 24;
-                            if ((sc & B2J_CONST_EXC_MASK) == 0u) cr -= cr_exception(r, g);
-                            acc_h += cr;
+                uint32_t cr[V][4];
+#pragma unroll
+                for (int v = 0; v < V; v++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        cr[v][i] = scr[v][i] >> 24;
+                        if ((scr[v][i] & B2J_CONST_EXC_MASK) == 0u) {
+                            const uint8_t *px = raw + (ry * V + v) * kRawPitch + grp * 12 + i * 3;
+                            cr[v][i] -= cr_exception(px[0], px[1]);
                         }
-                        acc_v += H == 2 ? acc_h >> 1 : acc_h;
                     }
-                    s_cr[ry * TS::kCW + grp * kSamples + c] = (uint8_t)(V == 2 ? acc_v >> 1 : acc_v);
+                if (H == 1) {
+                    *reinterpret_cast<uint32_t *>(s_cr + ry * TS::kCW + grp * 4) =
+                        cr[0][0] | (cr[0][1] << 8) | (cr[0][2] << 16) | (cr[0][3] << 24);
+                } else {
+                    uint32_t c0 = (cr[0][0] + cr[0][1]) >> 1, c1 = (cr[0][2] + cr[0][3]) >> 1;
+                    if (V == 2) {
+                        c0 = (c0 + ((cr[V - 1][0] + cr[V - 1][1]) >> 1)) >> 1;
+                        c1 = (c1 + ((cr[V - 1][2] + cr[V - 1][3]) >> 1)) >> 1;
+                    }
+                    *reinterpret_cast<uint16_t *>(s_cr + ry * TS::kCW + grp * 2) = (uint16_t)(c0 | (c1 << 8));
                 }
             }
         }
