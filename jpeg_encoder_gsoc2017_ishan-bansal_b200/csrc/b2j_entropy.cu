@@ -304,12 +304,14 @@ static int scan_chunks(long long nblk) { return (int)((nblk + kScanChunk - 1) / 
 
 int launch_stuffing(const uint8_t *unstuffed, const int64_t *total_bits, uint32_t *ffpart, int64_t *sizes, uint8_t *out,
                     long long ucap, long long out_cap, int n_frames, const HeaderParam &H, const int *error_flag,
-                    cudaStream_t st)
+                    bool counted, cudaStream_t st)
 {
     const int schunks = stuff_chunks(ucap);
     dim3 sgrid((unsigned)schunks, (unsigned)n_frames);
-    k_ff_count<<<sgrid, 256, 0, st>>>(unstuffed, total_bits, ffpart, ucap, schunks);
-    B2J_LAUNCH_CHECK("k_ff_count");
+    if (!counted) {
+        k_ff_count<<<sgrid, 256, 0, st>>>(unstuffed, total_bits, ffpart, ucap, schunks);
+        B2J_LAUNCH_CHECK("k_ff_count");
+    }
     k_ff_scan<<<(unsigned)n_frames, 256, 0, st>>>(ffpart, total_bits, sizes, ucap, out_cap, schunks, kHeaderBytes, error_flag);
     B2J_LAUNCH_CHECK("k_ff_scan");
     k_stuff_write<<<sgrid, 256, 0, st>>>(unstuffed, total_bits, ffpart, sizes, out, ucap, out_cap, schunks, H);
@@ -404,5 +406,5 @@ extern "C" int b2j_bitpack(const int16_t *coefs, const uint32_t *offsets, const 
     if (zrl == B2J_ZRL_EAGER) k_bitpack<true><<<pgrid, kPackBlocks, 0, st>>>(coefs, offsets, total_bits, unstuffed, ucap, e, L);
     else k_bitpack<false><<<pgrid, kPackBlocks, 0, st>>>(coefs, offsets, total_bits, unstuffed, ucap, e, L);
     B2J_LAUNCH_CHECK("k_bitpack");
-    return launch_stuffing(unstuffed, total_bits, ffpart, sizes, out, ucap, out_cap, g.n_frames, H, nullptr, st);
+    return launch_stuffing(unstuffed, total_bits, ffpart, sizes, out, ucap, out_cap, g.n_frames, H, nullptr, false, st);
 }

@@ -133,8 +133,10 @@ static inline int stuff_chunks(long long ucap) { return (int)((ucap + kStuffChun
 
 // 0xFF stuffing + JFIF framing of n_frames unstuffed streams (b2j_entropy.cu).
 // error_flag may be null; when *error_flag != 0 every sizes[f] is set to INT64_MIN.
+// counted: ffpart already holds the 0xFF count of every 4096-byte chunk (the fused entropy kernel
+// counts while it composes the words), so the counting pass is skipped.
 int launch_stuffing(const uint8_t *unstuffed, const int64_t *total_bits, uint32_t *ffpart, int64_t *sizes, uint8_t *out,
                     long long ucap, long long out_cap, int n_frames, const HeaderParam &H, const int *error_flag,
-                    cudaStream_t st);
+                    bool counted, cudaStream_t st);
 
 }  // namespace b2j

@@ -42,6 +42,8 @@ struct FusedEntropyParams {
     unsigned int *ticket;
     int *error_flag;
     uint32_t *overflow;           // [gridDim.x][kOvfWords][kCols]
+    uint32_t *ffpart;             // [n_frames][schunks]: 0xFF bytes per 4096-byte chunk of the packed stream (zeroed)
+    int schunks;
     long long ucap;
     int chunks;
     EGeo e;
@@ -314,7 +316,14 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
                 v |= s_priv[nb] >> have;
                 have += (int)s_nbits[nb];
             }
-            if (w < wcap) dst[w] = __byte_perm(v, 0u, 0x0123);      // big-endian bytes
+            if (w < wcap) {
+                dst[w] = __byte_perm(v, 0u, 0x0123);                 // big-endian bytes
+                const uint32_t z = ~v;                               // a zero byte of z is a 0xFF byte of the stream
+                if ((z - 0x01010101u) & ~z & 0x80808080u) {
+                    const uint32_t n = ((z & 0xFFu) == 0u) + ((z & 0xFF00u) == 0u) + ((z & 0xFF0000u) == 0u) + ((z >> 24) == 0u);
+                    atomicAdd(P.ffpart + (long long)f * P.schunks + (int)(w >> 10), n);      // 1024 words per stuffing chunk
+                }
+            }
         }
     }
   }
@@ -330,17 +339,27 @@ static size_t fused_status_bytes(const Geo &g)
     return 256 + (size_t)g.n_frames * chunks * sizeof(unsigned long long);
 }
 
+struct FusedWs { size_t status, ffpart, zero_bytes, total_bits, unstuffed, overflow, total; };
+
+static FusedWs fused_ws(const Geo &g, long long ucap)
+{
+    FusedWs w;
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    w.status = 256;                                                     // [0,256): ticket, error flag
+    w.ffpart = up(w.status + fused_status_bytes(g) - 256);
+    w.zero_bytes = up(w.ffpart + (size_t)g.n_frames * stuff_chunks(ucap) * sizeof(uint32_t));   // [0, zero_bytes) is cleared per call
+    w.total_bits = w.zero_bytes;
+    w.unstuffed = up(w.total_bits + (size_t)g.n_frames * sizeof(int64_t));
+    w.overflow = up(w.unstuffed + (size_t)g.n_frames * (size_t)ucap);
+    w.total = w.overflow + (size_t)kMaxSlots * kOvfWords * kCols * sizeof(uint32_t);
+    return w;
+}
+
 extern "C" size_t b2j_entropy_workspace_bytes(const b2j_image_desc *desc, int64_t out_cap)
 {
     Geo g;
     if (make_geo(desc, &g) || out_cap < kHeaderBytes + 2) return 0;
-    const long long ucap = ucap_of(out_cap);
-    size_t o = (fused_status_bytes(g) + 255) & ~(size_t)255;
-    o += ((size_t)g.n_frames * sizeof(int64_t) + 255) & ~(size_t)255;
-    o += (size_t)g.n_frames * (size_t)ucap;
-    o += ((size_t)g.n_frames * stuff_chunks(ucap) * sizeof(uint32_t) + 511) & ~(size_t)255;
-    o += (size_t)kMaxSlots * kOvfWords * kCols * sizeof(uint32_t);
-    return o;
+    return fused_ws(g, ucap_of(out_cap)).total;
 }
 
 // K2..K4 in one pass over the coefficients: coefs -> JFIF files.
@@ -360,20 +379,19 @@ extern "C" int b2j_entropy_encode(const int16_t *coefs, const b2j_image_desc *de
     const long long ucap = ucap_of(out_cap);
     const int chunks = (int)((g.blocks_per_frame + kChunk - 1) / kChunk);
     uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
-    const size_t status_bytes = fused_status_bytes(g);
+    const FusedWs W = fused_ws(g, ucap);
     FusedEntropyParams P;
     P.coefs = coefs;
     P.ticket = reinterpret_cast<unsigned int *>(ws);
     P.error_flag = reinterpret_cast<int *>(ws + 64);
-    P.status = reinterpret_cast<unsigned long long *>(ws + 256);
-    size_t o = (status_bytes + 255) & ~(size_t)255;
-    P.total_bits = reinterpret_cast<int64_t *>(ws + o);
-    o += ((size_t)g.n_frames * sizeof(int64_t) + 255) & ~(size_t)255;
-    P.unstuffed = ws + o;
-    o += (size_t)g.n_frames * (size_t)ucap;
-    uint32_t *ffpart = reinterpret_cast<uint32_t *>(ws + o);
-    o += ((size_t)g.n_frames * stuff_chunks(ucap) * sizeof(uint32_t) + 511) & ~(size_t)255;
-    P.overflow = reinterpret_cast<uint32_t *>(ws + o);
+    P.status = reinterpret_cast<unsigned long long *>(ws + W.status);
+    P.ffpart = reinterpret_cast<uint32_t *>(ws + W.ffpart);
+    P.schunks = stuff_chunks(ucap);
+    P.total_bits = reinterpret_cast<int64_t *>(ws + W.total_bits);
+    P.unstuffed = ws + W.unstuffed;
+    P.overflow = reinterpret_cast<uint32_t *>(ws + W.overflow);
+    uint32_t *ffpart = P.ffpart;
+    const size_t status_bytes = W.zero_bytes;
     P.ucap = ucap;
     P.chunks = chunks;
     P.e = egeo_of(g);
@@ -403,5 +421,5 @@ extern "C" int b2j_entropy_encode(const int16_t *coefs, const b2j_image_desc *de
     if (zrl == B2J_ZRL_EAGER) k_entropy_fused<true><<<grid, kChunk, kFusedSmem, st>>>(P, L);
     else k_entropy_fused<false><<<grid, kChunk, kFusedSmem, st>>>(P, L);
     B2J_LAUNCH_CHECK("k_entropy_fused");
-    return launch_stuffing(P.unstuffed, P.total_bits, ffpart, sizes, out, ucap, out_cap, g.n_frames, H, P.error_flag, st);
+    return launch_stuffing(P.unstuffed, P.total_bits, ffpart, sizes, out, ucap, out_cap, g.n_frames, H, P.error_flag, true, st);
 }
