@@ -76,13 +76,17 @@ class OraclePort:
             if res.returncode:
                 raise RuntimeError("cannot build the C oracle: " + res.stderr)
         self.lib = ctypes.CDLL(path)
-        self.threads = int(self.lib.b2jo_num_threads())
+        # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1; that is not "all")
+        try:
+            self.threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            self.threads = os.cpu_count() or 1
 
     def encode_batch(self, frames_np, out_np, sizes_np, cap):
         n = frames_np.shape[0]
         rc = self.lib.b2jo_encode_batch(frames_np.ctypes.data_as(ctypes.c_void_p), n, H, W, int(SUB), QUALITY,
                                         0 if ZRL == "eager" else 1, out_np.ctypes.data_as(ctypes.c_void_p),
-                                        ctypes.c_int64(cap), sizes_np.ctypes.data_as(ctypes.c_void_p), 0)
+                                        ctypes.c_int64(cap), sizes_np.ctypes.data_as(ctypes.c_void_p), self.threads)
         assert rc == 0
 
 
@@ -339,7 +343,7 @@ def main():
                         "other instructions per 8x8 block-equivalent (DESIGN.md)"}
 
     base = None
-    if not args.skip_cpu_baseline:
+    if not args.skip_cpu_baseline and n_gpus == 1:        # reported on rank 0 at N = 1 only
         base, _ = cpu_baseline(host, 1)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
