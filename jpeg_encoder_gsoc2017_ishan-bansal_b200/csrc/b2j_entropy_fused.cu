@@ -289,39 +289,48 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
     const unsigned long long E = (unsigned long long)s_misc[5] | ((unsigned long long)s_misc[6] << 32);
 
     // ---- 4. compose the owned words.  Bit g of the frame's stream lives in word g >> 5.
+    // (bit offsets inside a frame fit 32 bits: make_geo() refuses larger frames)
     if (tid < nown) {
-        const unsigned long long G = E + excl;
-        unsigned long long Gn = G + (unsigned)mybits;
+        const uint32_t G = (uint32_t)E + excl;
+        uint32_t total = (uint32_t)mybits;
         if (last && tid == nown - 1) {                               // pad the final byte of the frame with 1s
-            const int pad = (int)((8ull - (Gn & 7ull)) & 7ull);
+            const int pad = (int)((8u - ((G + total) & 7u)) & 7u);
+            P.total_bits[f] = (int64_t)(G + total);
             if (pad) {
                 sink.put((1u << pad) - 1u, pad);
                 sink.flush();
-                Gn += (unsigned)pad;
+                total += (uint32_t)pad;
             }
-            P.total_bits[f] = (int64_t)(G + (unsigned)mybits);
         }
         uint32_t *dst = reinterpret_cast<uint32_t *>(P.unstuffed + (long long)f * P.ucap);
-        const unsigned long long wcap = (unsigned long long)(P.ucap >> 2);
-        const int total = (int)(Gn - G);
-        for (unsigned long long w = (G + 31ull) >> 5; w < ((Gn + 31ull) >> 5); w++) {
-            const int rel = (int)((w << 5) - G);                     // first bit of this word inside my block
+        const uint32_t wcap = (uint32_t)(P.ucap >> 2);
+        uint32_t *ffp = P.ffpart + (long long)f * P.schunks;
+        const int nsucc = last ? nown : nall;                        // columns that may supply following bits
+        uint32_t w = (G + 31u) >> 5;
+        const uint32_t wend = (G + total + 31u) >> 5;
+        int rel = (int)((w << 5) - G);                               // first bit of word w inside my block
+        uint32_t a = sink.load(rel >> 5);
+#pragma unroll 1
+        for (; w < wend; w++, rel += 32) {
             const int k = rel >> 5, sh = rel & 31;
-            const uint32_t a = sink.load(k);
-            const uint32_t bnext = (k + 1) * 32 < total ? sink.load(k + 1) : 0u;
+            const int have0 = (int)total - rel;                      // my bits available from `rel`
+            const uint32_t bnext = have0 > 32 - sh ? sink.load(k + 1) : 0u;
             uint32_t v = __funnelshift_l(bnext, a, sh);
-            int have = total - rel;                                  // my bits available from `rel`
-            // complete the word with the first bits of the following blocks
-            for (int nb = tid + 1; have < 32 && nb < nall && !(last && nb >= nown); nb++) {
-                v |= s_priv[nb] >> have;
-                have += (int)s_nbits[nb];
+            a = bnext;
+            if (have0 < 32) {                                        // complete the word with the following blocks' first bits
+                int have = have0;
+#pragma unroll 1
+                for (int nb = tid + 1; have < 32 && nb < nsucc; nb++) {
+                    v |= s_priv[nb] >> have;
+                    have += (int)s_nbits[nb];
+                }
             }
             if (w < wcap) {
                 dst[w] = __byte_perm(v, 0u, 0x0123);                 // big-endian bytes
                 const uint32_t z = ~v;                               // a zero byte of z is a 0xFF byte of the stream
                 if ((z - 0x01010101u) & ~z & 0x80808080u) {
                     const uint32_t n = ((z & 0xFFu) == 0u) + ((z & 0xFF00u) == 0u) + ((z & 0xFF0000u) == 0u) + ((z >> 24) == 0u);
-                    atomicAdd(P.ffpart + (long long)f * P.schunks + (int)(w >> 10), n);      // 1024 words per stuffing chunk
+                    atomicAdd(ffp + (w >> 10), n);                   // 1024 words per stuffing chunk
                 }
             }
         }
