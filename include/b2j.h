@@ -103,6 +103,18 @@ int b2j_rgb2ycbcr(const uint8_t *rgb, uint8_t *y, uint8_t *cb, uint8_t *cr,
 int b2j_ycbcr444to422(const uint8_t *y, const uint8_t *cb, const uint8_t *cr,
                       uint8_t *y_out, uint8_t *cb_cr_out, int64_t n_pixels, void *stream);
 
+/* Decode-direction operators (they let the reference's round-trip benches
+ * test/ycbcr2rgb_tb.py and test/ycbcr_resampling_tb.py run against this library).
+ * replaces: YCbCr2RGB datapath, litejpeg/core/csc.py:219-310 (mode XAPP930 = XAPP931 integer
+ * pipeline, saturated) and RAWImage.ycbcr2rgb, test/common.py:172-178 (mode JFIF: float64,
+ * int(), not clamped - hence int16 outputs). */
+int b2j_ycbcr2rgb(const uint8_t *y, const uint8_t *cb, const uint8_t *cr,
+                  int16_t *r, int16_t *g, int16_t *b, int64_t n_pixels, int mode, void *stream);
+
+/* replaces: YCbCr422to444 datapath, litejpeg/core/crs.py:88-146 (sample repeat). */
+int b2j_ycbcr422to444(const uint8_t *y, const uint8_t *cb_cr,
+                      uint8_t *y_out, uint8_t *cb_out, uint8_t *cr_out, int64_t n_pixels, void *stream);
+
 /* [ext] plane subsampling with the same pair mean, horizontally (422) and then
  * vertically (420).  in: height x width, out: (height/v) x (width/2). */
 int b2j_chroma_subsample(const uint8_t *in, uint8_t *out, int32_t height, int32_t width,

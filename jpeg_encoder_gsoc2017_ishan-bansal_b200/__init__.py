@@ -7,7 +7,7 @@ from . import _lib                                                     # noqa: F
 from ._lib import B2JError, build, lib, make_desc, geometry, quant_tables   # noqa: F401
 from .common import (Packet, coef, rgb_layout, ycbcr444_layout, ycbcr422_layout, dct_block_layout,   # noqa: F401
                      block_layout, to_signed, to_unsigned)
-from .core import (RGB2YCbCr, rgb2ycbcr_coefs, YCbCr444to422, YCbCr444to420, DCT, Quantization, quant_values,  # noqa: F401
+from .core import (RGB2YCbCr, YCbCr2RGB, rgb2ycbcr_coefs, ycbcr2rgb_coefs, YCbCr444to422, YCbCr422to444, YCbCr444to420, DCT, Quantization, quant_values,  # noqa: F401
                    ZigZag, zigzag_order, zigzag_rom, RunLength, EntropyCoder, RLEMain, Huffman, BitPack)
 from .encoder import JpegEncoder, ShardedJpegEncoder, shard_range, gather_sizes, gather_streams  # noqa: F401
 

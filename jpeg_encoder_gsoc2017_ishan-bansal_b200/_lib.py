@@ -45,6 +45,8 @@ SIGNATURES = {
     "b2j_quant_tables": (c_int, [c_int, _P, _P]),
     "b2j_rgb2ycbcr": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P]),
     "b2j_ycbcr444to422": (c_int, [_P, _P, _P, _P, _P, c_int64, _P]),
+    "b2j_ycbcr2rgb": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
+    "b2j_ycbcr422to444": (c_int, [_P, _P, _P, _P, _P, c_int64, _P]),
     "b2j_chroma_subsample": (c_int, [_P, _P, c_int32, c_int32, c_int32, _P]),
     "b2j_dct": (c_int, [_P, _P, c_int64, _P]),
     "b2j_quantize": (c_int, [_P, _P, c_int64, _P, c_int, _P]),

@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused_tiled(const __grid_consta
         // The fast path is straight-line integer code for all pixels of the item (no branches, so
         // the pixels interleave); the rare inputs where the float64 model differs from the exact
         // rational value are only flagged here and patched afterwards from the raw bytes.
-#pragma unroll 1
+#pragma unroll 1            // (unrolling by 2 pushes the kernel past the instruction cache: 1.56 -> 2.0 ms)
         for (int item = tid; item < 8 * (kTileW / 4); item += kThreads) {
             const int ry = item / (kTileW / 4), grp = item % (kTileW / 4);
             if (grp * 4 >= cur.need_px) continue;

@@ -36,6 +36,46 @@ __global__ void k_ycbcr444to422(const uint8_t *__restrict__ y, const uint8_t *__
     }
 }
 
+// ---- YCbCr2RGB (decode direction; litejpeg/core/csc.py:219-310 XAPP931 datapath with coef_w = 8:
+// acoef 116, bcoef -8, ccoef -27, dcoef 98, products >> 6, saturate; mode JFIF is the float64
+// inverse of test/common.py:172-178, int() truncation, NOT clamped - hence int16 outputs)
+__global__ void k_ycbcr2rgb(const uint8_t *__restrict__ y, const uint8_t *__restrict__ cb, const uint8_t *__restrict__ cr,
+                            int16_t *__restrict__ r, int16_t *__restrict__ g, int16_t *__restrict__ b, long long n, int mode)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int yy = y[i], cbm = (int)cb[i] - 128, crm = (int)cr[i] - 128;
+        int rr, gg, bb;
+        if (mode == B2J_CSC_XAPP930) {
+            const int ym = yy - 16;
+            rr = ym + ((crm * 116) >> 6);
+            gg = ym + ((cbm * -8) >> 6) + ((crm * -27) >> 6);
+            bb = ym + ((cbm * 98) >> 6);
+            rr = min(max(rr, 0), 255); gg = min(max(gg, 0), 255); bb = min(max(bb, 0), 255);
+        } else {
+            const double yd = (double)yy, cbd = (double)cbm, crd = (double)crm;
+            rr = __double2int_rz(__dadd_rn(yd, __dmul_rn(crd, 1.402)));
+            gg = __double2int_rz(__dadd_rn(__dadd_rn(yd, __dmul_rn(cbd, -0.34414)), __dmul_rn(crd, -0.71414)));
+            bb = __double2int_rz(__dadd_rn(yd, __dmul_rn(cbd, 1.772)));
+        }
+        r[i] = (int16_t)rr; g[i] = (int16_t)gg; b[i] = (int16_t)bb;
+    }
+}
+
+// ---- YCbCr422to444 (decode direction; litejpeg/core/crs.py:88-128): sample repeat
+__global__ void k_ycbcr422to444(const uint8_t *__restrict__ y, const uint8_t *__restrict__ cbcr, uint8_t *__restrict__ yo,
+                                uint8_t *__restrict__ cb, uint8_t *__restrict__ cr, long long npairs)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < npairs; i += stride) {
+        yo[2 * i] = y[2 * i]; yo[2 * i + 1] = y[2 * i + 1];
+        cb[2 * i] = cb[2 * i + 1] = cbcr[2 * i];
+        cr[2 * i] = cr[2 * i + 1] = cbcr[2 * i + 1];
+    }
+}
+
 // ---- [ext] plane subsampling: pair mean horizontally, then (4:2:0) vertically
 __global__ void k_chroma_subsample(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
                                    int height, int width, int v2)
@@ -162,6 +202,29 @@ extern "C" int b2j_ycbcr444to422(const uint8_t *y, const uint8_t *cb, const uint
     if (n_pixels == 0) return B2J_OK;
     k_ycbcr444to422<<<grid_for(n_pixels / 2, 256), 256, 0, as_stream(stream)>>>(y, cb, cr, y_out, cb_cr_out, n_pixels / 2);
     B2J_LAUNCH_CHECK("k_ycbcr444to422");
+    return B2J_OK;
+}
+
+extern "C" int b2j_ycbcr2rgb(const uint8_t *y, const uint8_t *cb, const uint8_t *cr, int16_t *r, int16_t *g, int16_t *b,
+                             int64_t n_pixels, int mode, void *stream)
+{
+    B2J_REQUIRE(y && cb && cr && r && g && b, B2J_E_ARG, "b2j_ycbcr2rgb: null pointer");
+    B2J_REQUIRE(n_pixels >= 0, B2J_E_ARG, "b2j_ycbcr2rgb: negative size");
+    B2J_REQUIRE(mode == B2J_CSC_JFIF || mode == B2J_CSC_XAPP930, B2J_E_ARG, "b2j_ycbcr2rgb: bad mode %d", mode);
+    if (n_pixels == 0) return B2J_OK;
+    k_ycbcr2rgb<<<grid_for(n_pixels, 256), 256, 0, as_stream(stream)>>>(y, cb, cr, r, g, b, n_pixels, mode);
+    B2J_LAUNCH_CHECK("k_ycbcr2rgb");
+    return B2J_OK;
+}
+
+extern "C" int b2j_ycbcr422to444(const uint8_t *y, const uint8_t *cb_cr, uint8_t *y_out, uint8_t *cb_out, uint8_t *cr_out,
+                                 int64_t n_pixels, void *stream)
+{
+    B2J_REQUIRE(y && cb_cr && y_out && cb_out && cr_out, B2J_E_ARG, "b2j_ycbcr422to444: null pointer");
+    B2J_REQUIRE(n_pixels >= 0 && n_pixels % 2 == 0, B2J_E_ARG, "b2j_ycbcr422to444: n_pixels must be even and >= 0");
+    if (n_pixels == 0) return B2J_OK;
+    k_ycbcr422to444<<<grid_for(n_pixels / 2, 256), 256, 0, as_stream(stream)>>>(y, cb_cr, y_out, cb_out, cr_out, n_pixels / 2);
+    B2J_LAUNCH_CHECK("k_ycbcr422to444");
     return B2J_OK;
 }
 

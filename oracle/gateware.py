@@ -60,6 +60,67 @@ def rgb2ycbcr_gateware_model(r, g, b, dw=8):
     return y, cb, cr
 
 
+def ycbcr2rgb_coefs(dw, cw=None):
+    """litejpeg/core/csc.py:194-216."""
+    ca, cb, cc, cd = 0.1819, 0.0618, 0.6495, 0.5512
+    xcoef_w = None if cw is None else cw - 2
+    return {
+        "ca": coef(ca, cw), "cb": coef(cb, cw), "cc": coef(cc, cw), "cd": coef(cd, cw),
+        "yoffset": 2 ** (dw - 4), "coffset": 2 ** (dw - 1),
+        "ymax": 2 ** dw - 1, "cmax": 2 ** dw - 1, "ymin": 0, "cmin": 0,
+        "acoef": coef(1 / cd, xcoef_w), "bcoef": coef(-cb / (cc * (1 - ca - cb)), xcoef_w),
+        "ccoef": coef(-ca / (cd * (1 - ca - cb)), xcoef_w), "dcoef": coef(1 / cc, xcoef_w),
+    }
+
+
+def ycbcr2rgb_gateware(y, cb, cr, ycbcr_w=8, rgb_w=8, coef_w=8):
+    """YCbCr2RGBDatapath, litejpeg/core/csc.py:219-310 (XAPP931): products sliced [coef_w-2:]
+    (arithmetic shift once re-interpreted in the signed sum), saturated to 0..2^rgb_w-1."""
+    c = ycbcr2rgb_coefs(rgb_w, coef_w)
+    sh = coef_w - 2
+    y = np.asarray(y).astype(np.int64)
+    cb = np.asarray(cb).astype(np.int64)
+    cr = np.asarray(cr).astype(np.int64)
+    cbm, crm, ym = cb - c["coffset"], cr - c["coffset"], y - c["yoffset"]     # :266-283
+    r = ym + ((crm * c["acoef"]) >> sh)                                       # :291-297
+    g = ym + ((cbm * c["bcoef"]) >> sh) + ((crm * c["ccoef"]) >> sh)
+    b = ym + ((cbm * c["dcoef"]) >> sh)
+    hi = 2 ** rgb_w - 1
+    return np.clip(r, 0, hi), np.clip(g, 0, hi), np.clip(b, 0, hi)            # :301-305
+
+
+def ycbcr2rgb_gateware_model(y, cb, cr, dw=8):
+    """test/common.py:158-168 `RAWImage.ycbcr2rgb_model`: float coefficients, int(), no clamp."""
+    c = ycbcr2rgb_coefs(dw)
+    y = np.asarray(y).astype(np.float64)
+    cb = np.asarray(cb).astype(np.float64)
+    cr = np.asarray(cr).astype(np.float64)
+    r = np.trunc(y - c["yoffset"] + (cr - c["coffset"]) * c["acoef"])
+    g = np.trunc(y - c["yoffset"] + (cb - c["coffset"]) * c["bcoef"] + (cr - c["coffset"]) * c["ccoef"])
+    b = np.trunc(y - c["yoffset"] + (cb - c["coffset"]) * c["dcoef"])
+    return r.astype(np.int64), g.astype(np.int64), b.astype(np.int64)
+
+
+def ycbcr2rgb_jfif(y, cb, cr):
+    """test/common.py:172-178 `RAWImage.ycbcr2rgb` (the Wikipedia inverse): float64, int(), no clamp."""
+    y = np.asarray(y).astype(np.float64)
+    cb = np.asarray(cb).astype(np.float64)
+    cr = np.asarray(cr).astype(np.float64)
+    r = np.trunc(y + (cr - 128) * 1.402)
+    g = np.trunc(y + (cb - 128) * -0.34414 + (cr - 128) * -0.71414)
+    b = np.trunc(y + (cb - 128) * 1.772)
+    return r.astype(np.int64), g.astype(np.int64), b.astype(np.int64)
+
+
+def ycbcr422to444(y, cb_cr):
+    """YCbCr422to444Datapath, litejpeg/core/crs.py:88-128: sample repeat; the even pixel of a
+    pair carries Cb, the odd one Cr."""
+    y = np.asarray(y).astype(np.int64)
+    cc = np.asarray(cb_cr).astype(np.int64)
+    assert y.size % 2 == 0
+    return y, np.repeat(cc[0::2], 2), np.repeat(cc[1::2], 2)
+
+
 def ycbcr444to422(y, cb, cr):
     """YCbCr444to422Datapath, litejpeg/core/crs.py:38-65.
 

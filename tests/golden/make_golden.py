@@ -43,6 +43,19 @@ import reference as refvec  # noqa: E402  (test/model/reference.py)
 
 from oracle import model_np as M  # noqa: E402
 
+# litejpeg/core/csc.py cannot be imported (it needs LiteX), but its coefficient helper is plain
+# Python: execute just that function (and `coef` from core/common.py) from the reference source.
+_ns = {}
+_src = open(os.path.join(REF, "litejpeg", "core", "common.py")).read()
+exec(_src[_src.index("def coef("):_src.index("def rgb_layout(")], _ns)
+_src = open(os.path.join(REF, "litejpeg", "core", "csc.py")).read()
+exec(_src[_src.index("def ycbcr2rgb_coefs("):_src.index("@CEInserter()", _src.index("def ycbcr2rgb_coefs("))], _ns)
+exec(_src[_src.index("def rgb2ycbcr_coefs("):_src.index("datapath_latency")], _ns)
+_mod = types.ModuleType("litejpeg_csc_coefs")
+_mod.ycbcr2rgb_coefs = _ns["ycbcr2rgb_coefs"]
+_mod.rgb2ycbcr_coefs = _ns["rgb2ycbcr_coefs"]
+sys.modules["litejpeg_csc_coefs"] = _mod
+
 rng = np.random.default_rng(20171019)
 meta = {}
 
@@ -191,6 +204,13 @@ raw = refcommon.RAWImage({"ca": 0.1819, "cb": 0.0618, "cc": 0.6495, "cd": 0.5512
 fx["raw64_rgb"] = np.array([raw.r, raw.g, raw.b])
 fx["raw64_ycbcr_xapp930_model"] = np.array(raw.rgb2ycbcr_model())
 fx["raw64_ycbcr_jfif"] = np.array(raw.rgb2ycbcr())
+# decode direction: both inverse colour models of RAWImage (test/common.py:158-178)
+raw.rgb2ycbcr()
+fx["raw64_rgb_from_jfif_via_wikipedia"] = np.array(raw.ycbcr2rgb())
+from litejpeg_csc_coefs import ycbcr2rgb_coefs as _c2  # noqa: E402  (copied constants, see below)
+raw2 = refcommon.RAWImage(_c2(8), os.path.join(REF, "test", "lena.png"), 64)
+raw2.rgb2ycbcr()
+fx["raw64_rgb_from_jfif_via_xapp931_model"] = np.array(raw2.ycbcr2rgb_model())
 np.savez_compressed(os.path.join(HERE, "reference_fixtures.npz"), **fx)
 meta["rle_names"] = rle_names
 

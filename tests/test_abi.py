@@ -81,6 +81,8 @@ def test_operator_surface_matches_the_reference(lj):
     assert lj.RGB2YCbCr(rgb_w=8, ycbcr_w=8, coef_w=8).latency == 8
     assert lj.RGB2YCbCr().sink_layout == [("r", 8), ("g", 8), ("b", 8)]
     assert lj.RGB2YCbCr().source_layout == [("y", 8), ("cb", 8), ("cr", 8)]
+    assert lj.YCbCr2RGB(ycbcr_w=8, rgb_w=8, coef_w=8).sink_layout == [("y", 8), ("cb", 8), ("cr", 8)]
+    assert lj.YCbCr422to444(dw=8).latency == 2 and lj.ycbcr2rgb_coefs(8, 8)["dcoef"] == 98
     assert lj.YCbCr444to422(dw=8).latency == 3 and lj.YCbCr444to422().source_layout == [("y", 8), ("cb_cr", 8)]
     assert lj.DCT(dw=12, dct_block=64).latency == 8 and lj.DCT().sink_layout == [("data", 12)]
     assert lj.Quantization().table == lj.quant_values and lj.quant_values[:3] == [16, 11, 10]

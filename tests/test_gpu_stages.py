@@ -69,6 +69,37 @@ def test_ycbcr_resampling_tb(lj, golden):
         assert np.array_equal(got, exp)
 
 
+def test_ycbcr2rgb_tb(lj, golden):
+    """test/ycbcr2rgb_tb.py: lena 64x64 (y, cb, cr) words through YCbCr2RGB() (decode direction)."""
+    ycc = golden.ref["raw64_ycbcr_jfif"]
+    pkt = lj.Packet(pack24(ycc[0], ycc[1], ycc[2]))
+    out = lj.YCbCr2RGB().process(pkt)                                # gateware datapath (XAPP931)
+    exp = GW.ycbcr2rgb_gateware(ycc[0], ycc[1], ycc[2])
+    assert np.array_equal(np.stack(unpack24(out)), np.stack(exp))
+    dev = torch.from_numpy(np.ascontiguousarray(ycc.T)).to(torch.uint8).cuda()
+    got = lj.YCbCr2RGB(model="jfif").process(dev).cpu().numpy().T     # float model, fixture of the reference, unclamped
+    assert np.array_equal(got, golden.ref["raw64_rgb_from_jfif_via_wikipedia"])
+    # every (y, cb, cr) triple, both models
+    allv = torch.arange(1 << 24, dtype=torch.int64, device="cuda")
+    trip = torch.stack([(allv >> 16) & 255, (allv >> 8) & 255, allv & 255], dim=1).to(torch.uint8)
+    a = trip.cpu().numpy().astype(np.int64)
+    for model, fn in (("xapp931", GW.ycbcr2rgb_gateware), ("jfif", GW.ycbcr2rgb_jfif)):
+        got = lj.YCbCr2RGB(model=model).process(trip).cpu().numpy().astype(np.int64)
+        exp = np.stack(fn(a[:, 0], a[:, 1], a[:, 2]), 1)
+        assert np.array_equal(got, exp), model
+
+
+def test_ycbcr_resampling_roundtrip_tb(lj, golden):
+    """test/ycbcr_resampling_tb.py chains YCbCr444to422 -> YCbCr422to444."""
+    ycc = golden.ref["raw64_ycbcr_jfif"]
+    mid = lj.YCbCr444to422().process(lj.Packet(pack24(ycc[0], ycc[1], ycc[2])))
+    out = lj.YCbCr422to444().process(mid)
+    ey, ecc = GW.ycbcr444to422(ycc[0], ycc[1], ycc[2])
+    exp = GW.ycbcr422to444(ey, ecc)
+    assert np.array_equal(np.stack(unpack24(out)), np.stack(exp))
+    assert np.array_equal(np.stack(unpack24(out))[0], ycc[0])        # luma is untouched
+
+
 def test_new_dct_tb2(lj, golden):
     """test/new_dct_tb2.py: DCTData.input_dct through DCT(); the model output is the pin."""
     out = lj.DCT().process(lj.Packet(golden.ref["dct_input"].tolist()))

@@ -79,6 +79,18 @@ def test_reference_fixture_classes(golden):
     assert np.abs(gw - np.clip(r["raw64_ycbcr_xapp930_model"], 0, 255)).max() <= 2
 
 
+def test_decode_direction_models(golden):
+    r = golden.ref
+    ycc = r["raw64_ycbcr_jfif"]
+    assert np.array_equal(np.stack(GW.ycbcr2rgb_jfif(*ycc)), r["raw64_rgb_from_jfif_via_wikipedia"])
+    assert np.array_equal(np.stack(GW.ycbcr2rgb_gateware_model(*ycc)), r["raw64_rgb_from_jfif_via_xapp931_model"])
+    gw = np.stack(GW.ycbcr2rgb_gateware(*ycc))
+    assert np.abs(gw - np.clip(r["raw64_rgb_from_jfif_via_xapp931_model"], 0, 255)).max() <= 1
+    assert GW.ycbcr2rgb_coefs(8, 8)["acoef"] == 116 and GW.ycbcr2rgb_coefs(8, 8)["ccoef"] == -27
+    y, cb, cr = GW.ycbcr422to444(*GW.ycbcr444to422(*ycc))
+    assert np.array_equal(y, ycc[0]) and (cb[0::2] == cb[1::2]).all()
+
+
 def test_reference_py_vectors(golden):
     r = golden.ref
     # test/model/reference.py: quant->zigzag vectors are exact; the colour vectors are only within
