@@ -10,7 +10,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_HERE, "libb2j.so")
+LIB_PATH = os.environ.get("B2J_LIB") or os.path.join(_HERE, "libb2j.so")   # B2J_LIB: kernel-variant experiments
 
 c_void_p, c_int, c_int32, c_int64, c_size_t = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int32,
                                                ctypes.c_int64, ctypes.c_size_t)

@@ -180,9 +180,21 @@ __global__ void __launch_bounds__(128) k_fused_simple(const __grid_constant__ Fu
 }
 
 // =============================================================== tiled variant
-constexpr int kTileW = 1024;                 // pixels
+// Tile width / CTA size / occupancy hint are compile-time knobs (profiles/scripts/k1_variants.py):
+// measured on B200 for 4:2:0: 1024 px x 128 threads x 3 CTAs/SM is the best of the variants tried
+// (512-px tiles -7 %, 192 or 256 threads -6 % / -30 %, 8-row band loads with 4 CTAs/SM -16 %).
+#ifndef B2J_TILE_W
+#define B2J_TILE_W 1024
+#endif
+#ifndef B2J_K1_THREADS
+#define B2J_K1_THREADS 128
+#endif
+#ifndef B2J_K1_MIN_CTAS
+#define B2J_K1_MIN_CTAS 2
+#endif
+constexpr int kTileW = B2J_TILE_W;           // pixels
 constexpr int kRawPitch = kTileW * 3;        // bytes
-constexpr int kThreads = 128;
+constexpr int kThreads = B2J_K1_THREADS;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -242,45 +254,8 @@ __device__ __forceinline__ TileCoord tile_coord(const FusedParams &P, long long 
     return c;
 }
 
-// one pixel of a 12-byte group (4 pixels, 3 little-endian words)
-template <int I>
-__device__ __forceinline__ void px_from_group(const uint32_t (&w)[3], uint32_t &r, uint32_t &g, uint32_t &b)
-{
-    constexpr int j0 = 3 * I, j1 = 3 * I + 1, j2 = 3 * I + 2;
-    r = (w[j0 >> 2] >> (8 * (j0 & 3))) & 0xFFu;
-    g = (w[j1 >> 2] >> (8 * (j1 & 3))) & 0xFFu;
-    b = (w[j2 >> 2] >> (8 * (j2 & 3))) & 0xFFu;
-}
-
-struct Ycc { uint32_t y, cb, cr; };
-
-// crx: 256-entry shared-memory table of cr_exception_class(g).  Cr candidates (g == b with
-// r - g even) are common in real images, so they only cost one predicated table read; the
-// branch is taken for the eight special grey levels only.
-__device__ __forceinline__ Ycc convert(uint32_t r, uint32_t g, uint32_t b, const uint8_t *crx)
-{
-    const uint32_t sy = csc_sum_y(r, g, b), scb = csc_sum_cb(r, g, b), scr = csc_sum_cr(r, g, b);
-    Ycc o;
-    o.y = sy >> 24; o.cb = scb >> 24; o.cr = scr >> 24;
-    const uint32_t cls = (scr & B2J_CONST_EXC_MASK) == 0u ? (uint32_t)crx[g] : 0u;
-    if ((sy & B2J_CONST_EXC_MASK) == 0u) o.y = csc_y_fp64(r, g, b);
-    if (cls != 0u) o.cr -= cr_exception_apply(cls, r, g);
-    return o;
-}
-
-__device__ __forceinline__ void convert4(const uint8_t *p, Ycc (&o)[4], const uint8_t *crx)
-{
-    const uint32_t *q = reinterpret_cast<const uint32_t *>(p);
-    const uint32_t w[3] = {q[0], q[1], q[2]};
-    uint32_t r, g, b;
-    px_from_group<0>(w, r, g, b); o[0] = convert(r, g, b, crx);
-    px_from_group<1>(w, r, g, b); o[1] = convert(r, g, b, crx);
-    px_from_group<2>(w, r, g, b); o[2] = convert(r, g, b, crx);
-    px_from_group<3>(w, r, g, b); o[3] = convert(r, g, b, crx);
-}
-
 template <int H, int V>
-__global__ void __launch_bounds__(kThreads, 2) k_fused_tiled(const __grid_constant__ FusedParams P, long long n_tiles, int tiles_x)
+__global__ void __launch_bounds__(kThreads, B2J_K1_MIN_CTAS) k_fused_tiled(const __grid_constant__ FusedParams P, long long n_tiles, int tiles_x)
 {
     using TS = TileShape<H, V>;
     constexpr int BPM = H * V + 2;
@@ -294,9 +269,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_fused_tiled(const __grid_consta
     uint64_t *bar = reinterpret_cast<uint64_t *>(s_crx + 256);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    s_mul[tid] = P.qm.mul[tid >> 6][tid & 63];
-    s_crx[tid] = (uint8_t)cr_exception_class((uint32_t)tid);
-    s_crx[tid + 128] = (uint8_t)cr_exception_class((uint32_t)tid + 128u);
+    for (int i = tid; i < 128; i += kThreads) s_mul[i] = P.qm.mul[i >> 6][i & 63];
+    for (int i = tid; i < 256; i += kThreads) s_crx[i] = (uint8_t)cr_exception_class((uint32_t)i);
     if (tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -510,6 +484,9 @@ static int launch_fused(const FusedParams &P, const Geo &g, int variant, cudaStr
     B2J_CUDA(cudaFuncSetAttribute(k_fused_tiled<H, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS::kSmem));
     int per_sm = 2;
     B2J_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_tiled<H, V>, kThreads, TS::kSmem));
+#ifdef B2J_K1_MAX_CTAS
+    if (per_sm > B2J_K1_MAX_CTAS) per_sm = B2J_K1_MAX_CTAS;
+#endif
     if (per_sm < 1) per_sm = 1;
     const long long grid = n_tiles < (long long)per_sm * sms ? n_tiles : (long long)per_sm * sms;   // persistent CTAs
     k_fused_tiled<H, V><<<(unsigned)grid, kThreads, TS::kSmem, st>>>(P, n_tiles, tiles_x);
