@@ -100,10 +100,17 @@ __device__ __forceinline__ void dct_quant_block(const uint2 (&px)[8], P &p)
 #pragma unroll
     for (int x = 0; x < 8; x++) {
         int s[8];
+#ifndef B2J_ROW_SHIFT_MASK      // PRMT extraction: 1 op per byte instead of shift+mask (1.501 -> 1.476 ms)
+        s[0] = (int)__byte_perm(px[x].x, 0u, 0x4440) - 128; s[1] = (int)__byte_perm(px[x].x, 0u, 0x4441) - 128;
+        s[2] = (int)__byte_perm(px[x].x, 0u, 0x4442) - 128; s[3] = (int)__byte_perm(px[x].x, 0u, 0x4443) - 128;
+        s[4] = (int)__byte_perm(px[x].y, 0u, 0x4440) - 128; s[5] = (int)__byte_perm(px[x].y, 0u, 0x4441) - 128;
+        s[6] = (int)__byte_perm(px[x].y, 0u, 0x4442) - 128; s[7] = (int)__byte_perm(px[x].y, 0u, 0x4443) - 128;
+#else
         s[0] = (int)(px[x].x & 0xFFu) - 128; s[1] = (int)((px[x].x >> 8) & 0xFFu) - 128;
         s[2] = (int)((px[x].x >> 16) & 0xFFu) - 128; s[3] = (int)(px[x].x >> 24) - 128;
         s[4] = (int)(px[x].y & 0xFFu) - 128; s[5] = (int)((px[x].y >> 8) & 0xFFu) - 128;
         s[6] = (int)((px[x].y >> 16) & 0xFFu) - 128; s[7] = (int)(px[x].y >> 24) - 128;
+#endif
         dct_1d_int(s, m0[x], m4[x], m1[x], m2[x], m3[x], m5[x], m6[x], m7[x]);
     }
     emit_col_i<0>(m0, p);

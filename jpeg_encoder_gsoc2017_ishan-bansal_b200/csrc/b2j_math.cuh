@@ -5,8 +5,8 @@
 // * FP64: only __dadd_rn/__dsub_rn/__dmul_rn are used for the model's float
 //   operations, so nothing can be contracted into an FMA (the library is also
 //   built with -fmad=false).
-// * int <-> double conversions use exact magic-number adds on the FP64 pipe
-//   (64 lanes/clk/SM on B200) instead of I2F/F2I.F64 (16 lanes/clk/SM); see
+// * double -> int uses an exact magic-number add on the FP64 pipe (one DADD.RZ gives
+//   floor(|v|/8)); int -> double uses I2F.F64 (see i2d below); pipe rates in
 //   profiles/r01/microbench_pipe_tput2.txt.
 #pragma once
 #include <stdint.h>
@@ -114,10 +114,17 @@ __device__ __forceinline__ uint32_t rgb2ycbcr_xapp930_px(int r, int g, int b)
 }
 
 // ---------------------------------------------------------------- conversions
-// exact (double)x for any int32: 2^52 + 2^31 + x is exact in the mantissa.
+// exact (double)x.  I2F.F64.S32 runs on the XU pipe (16 lanes/clk/SM) but is ONE instruction; the
+// magic-number form (2^52 + 2^31 + x) - (2^52 + 2^31) stays on the 4x faster FP64 pipe but costs three
+// issue slots (LOP3 + MOV of the high word + DADD).  K1 is issue-bound and the XU pipe idle, so the
+// hardware conversion wins: 1.556 -> 1.497 ms (profiles/scripts/k1_variants.py).
 __device__ __forceinline__ double i2d(int x)
 {
+#ifdef B2J_I2D_MAGIC
     return __dadd_rn(__hiloint2double(0x43300000, x ^ (int)0x80000000), -4503601774854144.0);
+#else
+    return __int2double_rn(x);
+#endif
 }
 // floor(|v| / 8) for |v| < 2^34: adding 2^55 leaves an ulp of 8, RZ truncates.
 __device__ __forceinline__ uint32_t abs_div8_trunc(double v)
