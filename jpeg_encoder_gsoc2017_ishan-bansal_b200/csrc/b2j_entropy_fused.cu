@@ -290,18 +290,26 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
 
     // ---- 4. compose the owned words.  Bit g of the frame's stream lives in word g >> 5.
     // (bit offsets inside a frame fit 32 bits: make_geo() refuses larger frames)
-    if (tid < nown) {
-        const uint32_t G = (uint32_t)E + excl;
-        uint32_t total = (uint32_t)mybits;
-        if (last && tid == nown - 1) {                               // pad the final byte of the frame with 1s
+    // The last block of the frame pads the final byte with 1s in its private column first; the
+    // barrier makes the padded word visible to the thread that composes the frame's final word
+    // (an earlier thread, when the last blocks are short).
+    uint32_t total = (uint32_t)mybits;
+    if (last) {
+        if (tid == nown - 1) {
+            const uint32_t G = (uint32_t)E + excl;
             const int pad = (int)((8u - ((G + total) & 7u)) & 7u);
             P.total_bits[f] = (int64_t)(G + total);
             if (pad) {
                 sink.put((1u << pad) - 1u, pad);
                 sink.flush();
                 total += (uint32_t)pad;
+                s_nbits[tid] = total;
             }
         }
+        __syncthreads();
+    }
+    if (tid < nown) {
+        const uint32_t G = (uint32_t)E + excl;
         uint32_t *dst = reinterpret_cast<uint32_t *>(P.unstuffed + (long long)f * P.ucap);
         const uint32_t wcap = (uint32_t)(P.ucap >> 2);
         uint32_t *ffp = P.ffpart + (long long)f * P.schunks;
