@@ -290,24 +290,13 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
 
     // ---- 4. compose the owned words.  Bit g of the frame's stream lives in word g >> 5.
     // (bit offsets inside a frame fit 32 bits: make_geo() refuses larger frames)
-    // The last block of the frame pads the final byte with 1s in its private column first; the
-    // barrier makes the padded word visible to the thread that composes the frame's final word
-    // (an earlier thread, when the last blocks are short).
-    uint32_t total = (uint32_t)mybits;
-    if (last) {
-        if (tid == nown - 1) {
-            const uint32_t G = (uint32_t)E + excl;
-            const int pad = (int)((8u - ((G + total) & 7u)) & 7u);
-            P.total_bits[f] = (int64_t)(G + total);
-            if (pad) {
-                sink.put((1u << pad) - 1u, pad);
-                sink.flush();
-                total += (uint32_t)pad;
-                s_nbits[tid] = total;
-            }
-        }
-        __syncthreads();
-    }
+    // The frame's final byte is padded with 1s by whichever thread composes the frame's final word:
+    // that is not always the last block's thread, nor even a thread of the last chunk (a short
+    // tail of 4-6 bit blocks can sit entirely inside a word owned by the previous chunk, which
+    // sees those blocks as its lookahead columns).
+    const uint32_t total = (uint32_t)mybits;
+    const bool reaches_end = bl >= e.nblk;                           // columns 0..nall-1 run to the frame's end
+    if (last && tid == nown - 1) P.total_bits[f] = (int64_t)((uint32_t)E + excl + total);
     if (tid < nown) {
         const uint32_t G = (uint32_t)E + excl;
         uint32_t *dst = reinterpret_cast<uint32_t *>(P.unstuffed + (long long)f * P.ucap);
@@ -331,6 +320,10 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
                 for (int nb = tid + 1; have < 32 && nb < nsucc; nb++) {
                     v |= s_priv[nb] >> have;
                     have += (int)s_nbits[nb];
+                }
+                if (have < 32 && reaches_end) {                      // ran out of blocks: this is the frame's final word
+                    const int pad = (8 - (have & 7)) & 7;
+                    v |= ((1u << pad) - 1u) << (32 - have - pad);
                 }
             }
             if (w < wcap) {

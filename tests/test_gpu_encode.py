@@ -99,6 +99,22 @@ def test_full_encode_bytes_equal_oracle(lj, oracle_c, sub, kind):
             assert f == oracle_c.encode_jpeg(frames[i].numpy(), sub, q, 0 if zrl == "eager" else 1), (q, zrl, i)
 
 
+@pytest.mark.parametrize("sub", SUBS)
+def test_flat_frames_short_final_blocks(lj, oracle_c, sub):
+    """Flat frames: every block after the first is 4-6 bits long, so the frame's final 32-bit word
+    (with the 1-padding) is composed by a thread that owns none of the last blocks."""
+    for (h, w) in ((8, 8), (16, 16), (24, 40), (136, 200), (264, 1032)):
+        frames = torch.empty(5, h, w, 3, dtype=torch.uint8)
+        for i, rgb in enumerate(((0, 0, 0), (255, 255, 255), (128, 128, 128), (200, 30, 90), (1, 254, 7))):
+            frames[i] = torch.tensor(rgb, dtype=torch.uint8)
+        frames[3, h - 1, w - 1, 0] = 17          # one busy block at the very end of one frame
+        for zrl in ("eager", "standard"):
+            enc = lj.JpegEncoder(sub, quality=75, zrl=zrl, out_cap=h * w * 8 + 4096)
+            files = enc.encode(frames.cuda())
+            for i, f in enumerate(files):
+                assert f == oracle_c.encode_jpeg(frames[i].numpy(), sub, 75, 0 if zrl == "eager" else 1), (h, w, zrl, i)
+
+
 def test_colour_exception_inputs_through_the_fused_kernel(lj, oracle_c):
     """Every input where the float64 colour model differs from the exact rational value (3464 for
     Y, 688 for Cr) plus look-alike candidates, laid out as an image: the fused kernel's patch-up
