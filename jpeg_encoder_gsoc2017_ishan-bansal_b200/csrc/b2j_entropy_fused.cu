@@ -18,6 +18,7 @@
 //   5. the last block of a frame pads the final byte with 1s; total_bits[frame] is written.
 // 0xFF stuffing and JFIF framing then run on the packed stream (launch_stuffing).
 #include "b2j_entropy.cuh"
+#include <cstdlib>
 
 namespace b2j {
 
@@ -424,6 +425,10 @@ extern "C" int b2j_entropy_encode(const int16_t *coefs, const b2j_image_desc *de
     } else {
         B2J_CUDA(cudaFuncSetAttribute(k_entropy_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem));
         B2J_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_entropy_fused<false>, kChunk, kFusedSmem));
+    }
+    if (const char *cap = getenv("B2J_ENT_CTAS_PER_SM")) {              // tuning knob: leave room for a concurrent kernel
+        const int c = atoi(cap);
+        if (c >= 1 && c < per_sm) per_sm = c;
     }
     long long slots = (long long)sms * (per_sm < 1 ? 1 : per_sm);
     if (slots > kMaxSlots) slots = kMaxSlots;

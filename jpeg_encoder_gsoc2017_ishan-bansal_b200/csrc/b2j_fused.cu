@@ -23,6 +23,7 @@
 //            buffer, so it overlaps (B), which is the long FP64 phase.
 #include "b2j_common.cuh"
 #include "b2j_math.cuh"
+#include <cstdlib>
 
 namespace b2j {
 
@@ -494,6 +495,10 @@ static int launch_fused(const FusedParams &P, const Geo &g, int variant, cudaStr
 #ifdef B2J_K1_MAX_CTAS
     if (per_sm > B2J_K1_MAX_CTAS) per_sm = B2J_K1_MAX_CTAS;
 #endif
+    if (const char *cap = getenv("B2J_K1_CTAS_PER_SM")) {               // tuning knob: leave room for a concurrent kernel
+        const int c = atoi(cap);
+        if (c >= 1 && c < per_sm) per_sm = c;
+    }
     if (per_sm < 1) per_sm = 1;
     const long long grid = n_tiles < (long long)per_sm * sms ? n_tiles : (long long)per_sm * sms;   // persistent CTAs
     k_fused_tiled<H, V><<<(unsigned)grid, kThreads, TS::kSmem, st>>>(P, n_tiles, tiles_x);
