@@ -31,7 +31,6 @@ import os
 import statistics
 import subprocess
 import sys
-import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -42,6 +41,17 @@ H, W, SUB, QUALITY, ZRL = 1080, 1920, "420", 75, "eager"
 FRAMES_PER_GPU = 256
 UNIQUE_FRAMES = 32
 CONFIG_IDX = 2
+KIND = "photo"
+WORKLOAD = "batch of %d synthetic 1920x1080 RGB frames per GPU, 4:2:0, quality 75 (BASELINE configs[2])"
+# The other BASELINE.json configs, for the per-config table in profiles/ (the driver's line is the default, configs[2]).
+# name: (height, width, subsampling, quality, frames per GPU, seed index, label)
+PRESETS = {
+    "1": (1080, 1920, "420", 75, 1, 1, "single synthetic 1920x1080 RGB frame, 4:2:0, quality 75 (BASELINE configs[1]); frames=%d"),
+    "2": (1080, 1920, "420", 75, 256, 2, WORKLOAD),
+    "3a": (2160, 3840, "444", 90, 64, 3, "batch of %d synthetic 3840x2160 frames per GPU, 4:4:4, quality 90 (BASELINE configs[3])"),
+    "3b": (2160, 3840, "420", 90, 64, 3, "batch of %d synthetic 3840x2160 frames per GPU, 4:2:0, quality 90 (BASELINE configs[3])"),
+    "4": (4320, 7680, "420", 75, 16, 4, "batch of %d synthetic 7680x4320 frames per GPU, 4:2:0, quality 75 (BASELINE configs[4])"),
+}
 METRIC = "Mpixel/s full JPEG encode (RGB -> JFIF bytes)"
 UNIT = "Mpixel/s"
 CPU_SAMPLE_FRAMES = 64
@@ -53,14 +63,25 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU (default: the named workload)")
+    ap.add_argument("--frames", type=int, default=None, help="frames per GPU (default: the named workload)")
+    ap.add_argument("--config", default="2", choices=sorted(PRESETS), help="BASELINE.json config (default 2, the headline)")
+    ap.add_argument("--kind", default="photo", choices=["photo", "noise", "grey"], help="synthetic content (SURVEY 8d stress)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
-    return ap.parse_args()
+    args = ap.parse_args()
+    global H, W, SUB, QUALITY, CONFIG_IDX, KIND, WORKLOAD, UNIQUE_FRAMES
+    H, W, SUB, QUALITY, frames, CONFIG_IDX, WORKLOAD = PRESETS[args.config]
+    KIND = args.kind
+    if args.frames is None:
+        args.frames = frames
+    UNIQUE_FRAMES = max(1, min(UNIQUE_FRAMES, (32 * 1080 * 1920) // (H * W)))     # bound the host-side generation time
+    if KIND != "photo":
+        WORKLOAD += " [content: %s]" % KIND
+    return args
 
 
 def workload_config(n_gpus, frames):
-    return {"workload": "batch of %d synthetic 1920x1080 RGB frames per GPU, 4:2:0, quality 75 (BASELINE configs[2])" % frames,
+    return {"workload": WORKLOAD % frames,
             "frames_per_gpu": frames, "global_frames": frames * n_gpus, "height": H, "width": W, "subsampling": SUB,
             "quality": QUALITY, "zrl_policy": ZRL, "unique_frames": min(UNIQUE_FRAMES, frames),
             "parallelism": "frames sharded across %d GPU(s), no data-path collective" % n_gpus,
@@ -94,9 +115,9 @@ def cpu_baseline(frames_torch, steps=1):
     """Times the oracle port on a bounded sample (first CPU_SAMPLE_FRAMES frames), all host threads."""
     import numpy as np
     port = OraclePort()
-    n = min(CPU_SAMPLE_FRAMES, frames_torch.shape[0])
+    n = max(1, min(CPU_SAMPLE_FRAMES * 1080 * 1920 // (H * W), frames_torch.shape[0]))
     sample = frames_torch[:n].numpy()
-    cap = H * W * 3 // 2 + 4096
+    cap = H * W * 3 + 4096
     out = np.zeros((n, cap), np.uint8)
     sizes = np.zeros(n, np.int64)
     port.encode_batch(sample[:min(8, n)], out, sizes, cap)          # warm-up (page faults, table init)
@@ -119,8 +140,8 @@ def run_reference_arm(args):
     import importlib
     import litejpeg_b200  # noqa: F401  (only for the synthetic frame generator; no GPU work on this arm)
     synth = importlib.import_module("litejpeg_b200.synth")
-    n = min(CPU_SAMPLE_FRAMES, args.frames)
-    frames = synth.batch(n, H, W, CONFIG_IDX, "photo", unique=min(UNIQUE_FRAMES, n))
+    n = max(1, min(CPU_SAMPLE_FRAMES * 1080 * 1920 // (H * W), args.frames))
+    frames = synth.batch(n, H, W, CONFIG_IDX, KIND, unique=min(UNIQUE_FRAMES, n))
     for _ in range(max(0, args.warmup - 1)):
         cpu_baseline(frames, 1)
     base, dt = cpu_baseline(frames, max(1, args.steps))
@@ -137,55 +158,73 @@ def run_reference_arm(args):
 
 # ---------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
-        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """Samples SM clock, power and throttle reasons of one GPU through NVML from a background thread
+    (every ~2 ms, so that even a 25 ms timed region holds samples).  `window()` brackets the timed
+    regions; the median is taken over the samples inside them."""
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
-    def __init__(self, gpu_indices):
-        self.gpus = set(gpu_indices)
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    def __init__(self, gpu_index):
+        import threading
+        self.samples, self.windows, self.err = [], [], None
+        self._stop = threading.Event()
+        self.thread = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(int(gpu_index))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+        except Exception as e:          # no NVML: report that, never fake a clock
+            self.err = repr(e)
+
+    def _run(self):
+        nv = self.nv
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                                     int(reasons(self.h)), nv.nvmlDeviceGetPowerUsage(self.h) / 1e3))
+            except Exception as e:
+                self.err = repr(e)
+                return
+            time.sleep(0.002)
+
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.p is None:
+        if self.thread is None:
+            out["error"] = self.err
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        clocks, mx, reasons, power = [], [], set(), []
-        for line in self.f:
-            parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 9:
-                continue
-            try:
-                idx = int(parts[0])
-                if idx not in self.gpus:
-                    continue
-                clocks.append(float(parts[1]))
-                mx.append(float(parts[2]))
-                power.append(float(parts[3]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        os.unlink(self.f.name)
-        if clocks:
-            busy = [c for c, p in zip(clocks, power) if p > 0.5 * max(power)] or clocks
-            out = {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                   "samples": len(clocks), "power_w_max": max(power)}
-        return out
+        self._stop.set()
+        self.thread.join(timeout=2)
+        inside = [x for x in self.samples if any(a <= x[0] <= b for a, b in self.windows)]
+        if not inside:
+            out["error"] = self.err or "no sample fell inside the timed regions"
+            return out
+        mask = 0
+        for x in inside:
+            mask |= x[2]
+        return {"sm_mhz": statistics.median(x[1] for x in inside), "sm_min_mhz": min(x[1] for x in inside),
+                "sm_max_mhz": self.max_mhz, "reasons": [n for bit, n in self.REASONS if mask & bit],
+                "samples": len(inside), "power_w_max": max(x[3] for x in inside),
+                "source": "NVML, ~2 ms period, samples inside the timed regions (device-timed steps and e2e)"}
 
 
 # ---------------------------------------------------------------------------------- GPU arm
+def _nvml_index(torch, cuda_index):
+    """NVML enumerates physical GPUs; CUDA_VISIBLE_DEVICES may renumber them."""
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        ids = [v.strip() for v in vis.split(",") if v.strip()]
+        if cuda_index < len(ids) and ids[cuda_index].isdigit():
+            return int(ids[cuda_index])
+    return cuda_index
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -211,7 +250,7 @@ def main():
 
     # ---- synthetic input (seeded per rank so every GPU has its own batch), pinned on the host
     host = torch.empty((frames, H, W, 3), dtype=torch.uint8).pin_memory()
-    synth.batch(frames, H, W, CONFIG_IDX + 100 * rank, "photo", unique=min(UNIQUE_FRAMES, frames), out=host)
+    synth.batch(frames, H, W, CONFIG_IDX + 100 * rank, KIND, unique=min(UNIQUE_FRAMES, frames), out=host)
     rgb = host.to(dev, non_blocking=True)
     torch.cuda.synchronize()
 
@@ -262,16 +301,19 @@ def main():
 
     for _ in range(args.warmup):
         step()
-    sampler = ClockSampler([local_rank] if world > 1 else [torch.cuda.current_device()]) if rank == 0 else None
+    sampler = ClockSampler(_nvml_index(torch, local_rank if world > 1 else torch.cuda.current_device())) if rank == 0 else None
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     barrier()
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
     t_start.record(stream)
     for k in range(args.steps):
         step(evs[k])
     t_end.record(stream)
     barrier()
+    if sampler:
+        sampler.window(w0, time.perf_counter())
     elapsed_ms = t_start.elapsed_time(t_end)
     stage_ms = [sum(e[i].elapsed_time(e[i + 1]) for e in evs) / args.steps for i in range(2)]
     if world > 1:
@@ -287,7 +329,7 @@ def main():
         out_host = torch.empty((frames, cap), dtype=torch.uint8).pin_memory()
         sizes_host = torch.empty((frames,), dtype=torch.int64)
         henc = lj.JpegEncoder(SUB, quality=QUALITY, zrl=ZRL, out_cap=cap)
-        fpc = 16
+        fpc = max(1, 16 * 1080 * 1920 // (H * W))
         for _ in range(2):
             henc.encode_host(host, out_host, sizes_host, frames_per_chunk=fpc)
         assert torch.equal(sizes_host, sz)
@@ -299,6 +341,8 @@ def main():
             henc.encode_host(host, out_host, sizes_host, frames_per_chunk=fpc)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        if sampler:
+            sampler.window(t0, t0 + dt)
         if world > 1:
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -324,16 +368,20 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     padded_px = frames * geo.padded_width * geo.padded_height
-    k1_bytes = padded_px * 6                      # 3 B/px RGB read + 1.5 coefficients/px * 2 B written (4:2:0)
+    coef_per_px = {"444": 3.0, "422": 2.0, "420": 1.5}[SUB]
+    k1_bytes = int(padded_px * (3 + 2 * coef_per_px))   # 3 B/px RGB read + int16 coefficients written (9 / 7 / 6 B per padded px)
     k1_ms = stage_ms[0]
     achieved = k1_bytes / (k1_ms / 1e3) / 1e9
     traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
-    except Exception:
-        pass
-    roofline = {"kernel": "k_fused_tiled<2,2> (K1: colour + 4:2:0 + float64 DCT + quantise + zig-zag)",
+    if args.config == "2" and KIND == "photo" and frames == FRAMES_PER_GPU:      # the capture was taken on this workload
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
+        except Exception:
+            pass
+    hv = {"444": "1,1", "422": "2,1", "420": "2,2"}[SUB]
+    roofline = {"kernel": "k_fused_tiled<%s> (K1: colour + chroma resampling + float64 DCT + quantise + zig-zag)" % hv,
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "frac_of_nominal_8000": achieved / 8000.0,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms,
                 "traffic": traffic["bytes_per_launch"] if traffic else None,

@@ -387,16 +387,29 @@ __global__ void __launch_bounds__(kThreads, B2J_K1_MIN_CTAS) k_fused_tiled(const
                 *reinterpret_cast<uint16_t *>(s_cb + ry * TS::kCW + grp * 2) = (uint16_t)(cb0 | (cb1 << 8));
                 *reinterpret_cast<uint16_t *>(s_cr + ry * TS::kCW + grp * 2) = (uint16_t)(cr0 | (cr1 << 8));
             }
-            // ---- rare patch-ups: the sums are still in registers, r/g/b are re-read from the raw bytes
+            // ---- patch-ups: the sums are still in registers, r and g are re-read from the raw words.
+            // Rare in noisy content, but every grey pixel (r = g = b) is a luma candidate, so this is
+            // branch-free per row: four independent table reads, one word store.
             if (!y_clean) {
 #pragma unroll
-                for (int v = 0; v < V; v++)
+                for (int v = 0; v < V; v++) {
+                    const uint32_t *q = reinterpret_cast<const uint32_t *>(raw + (ry * V + v) * kRawPitch + grp * 12);
+                    const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+                    uint32_t rg[4];                                   // r * 256 + g of the four pixels
+                    rg[0] = __byte_perm(w0, 0u, 0x4401);
+                    rg[1] = __byte_perm(w0, w1, 0x3434) & 0xFFFFu;
+                    rg[2] = __byte_perm(w1, 0u, 0x4423);
+                    rg[3] = __byte_perm(w2, 0u, 0x4412);
+                    uint32_t packed = 0u;
 #pragma unroll
-                    for (int i = 0; i < 4; i++)
-                        if ((sy[v][i] & B2J_CONST_EXC_MASK) == 0u) {
-                            const uint8_t *px = raw + (ry * V + v) * kRawPitch + grp * 12 + i * 3;
-                            s_y[(ry * V + v) * kTileW + grp * 4 + i] = (uint8_t)csc_y_fp64(px[0], px[1], px[2]);
-                        }
+                    for (int i = 0; i < 4; i++) {
+                        uint32_t bits = 0u;
+                        if ((sy[v][i] & B2J_CONST_EXC_MASK) == 0u) bits = __ldg(kYExceptionBits + (rg[i] >> 5));
+                        const uint32_t y = (sy[v][i] >> 24) - ((bits >> (rg[i] & 31u)) & 1u);
+                        packed |= y << (8 * i);
+                    }
+                    *reinterpret_cast<uint32_t *>(s_y + (ry * V + v) * kTileW + grp * 4) = packed;
+                }
             }
             if (cr_flag != 0u) {
                 uint32_t cr[V][4];

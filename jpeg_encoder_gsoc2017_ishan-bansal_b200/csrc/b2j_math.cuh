@@ -60,13 +60,18 @@ __device__ __forceinline__ uint32_t csc_sum_cr(uint32_t r, uint32_t g, uint32_t 
     return r * B2J_CONST_CX_HALF - g * B2J_CONST_CR_G - b * B2J_CONST_CR_B + B2J_CONST_C_OFFSET;
 }
 
-// The model's own expression for Y, for the rare candidates.
-static __device__ __noinline__ uint32_t csc_y_fp64(uint32_t r, uint32_t g, uint32_t b)
+// Where the float64 model yields Y one below the exact value: 3464 of the 16774 candidates.
+// Every (r, g) has at most one candidate b, so one bit per (r, g) decides (gen_y_exceptions.py
+// evaluates the model's own expression over all 2^24 inputs); 8 KB, read through L1 on the
+// candidate path only.  Candidates are rare in noisy content but include every grey pixel
+// (r = g = b), so the path has to stay cheap: a table read, not a float64 re-evaluation.
+static __device__ const uint32_t kYExceptionBits[2048] = {
+#include "b2j_y_exceptions.inc"
+};
+__device__ __forceinline__ uint32_t y_exception(uint32_t r, uint32_t g)
 {
-    double t = __dmul_rn(0.299, (double)r);
-    t = __dadd_rn(t, __dmul_rn(0.587, (double)g));
-    t = __dadd_rn(t, __dmul_rn(0.114, (double)b));
-    return (uint32_t)__double2int_rz(t);
+    const uint32_t idx = r * 256u + g;
+    return (__ldg(kYExceptionBits + (idx >> 5)) >> (idx & 31u)) & 1u;
 }
 
 // Where the float64 model yields Cr one below the exact value.  Only candidates
@@ -96,7 +101,7 @@ __device__ __forceinline__ uint32_t rgb2ycbcr_px(uint32_t r, uint32_t g, uint32_
 {
     uint32_t sy = csc_sum_y(r, g, b), scb = csc_sum_cb(r, g, b), scr = csc_sum_cr(r, g, b);
     uint32_t y = sy >> 24, cb = scb >> 24, cr = scr >> 24;
-    if ((sy & B2J_CONST_EXC_MASK) == 0u) y = csc_y_fp64(r, g, b);
+    if ((sy & B2J_CONST_EXC_MASK) == 0u) y -= y_exception(r, g);
     if ((scr & B2J_CONST_EXC_MASK) == 0u) cr -= cr_exception(r, g);
     return y | (cb << 8) | (cr << 16);
 }
