@@ -139,6 +139,12 @@ int b2j_zigzag(const int16_t *in, int16_t *out, int64_t n_blocks, void *stream);
 int b2j_run_length(const int16_t *in, uint32_t *words, int64_t n_blocks, int32_t prev_dc,
                    void *stream);
 
+/* replaces: rle_code, test/model/enc_frame.py:175-176 (the model's generic
+ * run-length code, itertools.groupby): (symbol, run) pairs, flattened.
+ * pairs: n_blocks x 128 int16 (only the first counts[b] values of row b are
+ * written); counts: n_blocks, the number of values (2 x pairs) of each block. */
+int b2j_rle_code(const int16_t *in, int16_t *pairs, int32_t *counts, int64_t n_blocks, void *stream);
+
 /* replaces: EntropyCoder, litejpeg/core/rle/entropycoder.py:19-65: size = bit
  * length of |x|. */
 int b2j_entropy_size(const int16_t *in, uint8_t *size, int64_t n, void *stream);

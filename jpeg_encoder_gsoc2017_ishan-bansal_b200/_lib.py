@@ -54,6 +54,7 @@ SIGNATURES = {
     "b2j_run_length": (c_int, [_P, _P, c_int64, c_int32, _P]),
     "b2j_entropy_size": (c_int, [_P, _P, c_int64, _P]),
     "b2j_rle_main": (c_int, [_P, _P, c_int64, c_int32, _P]),
+    "b2j_rle_code": (c_int, [_P, _P, _P, c_int64, _P]),
     "b2j_fused_block": (c_int, [_P, _DESC, _P, _P, _P, c_int, _P]),
     "b2j_block_bits": (c_int, [_P, _DESC, c_int, _P, _P]),
     "b2j_scan_workspace_bytes": (c_size_t, [_DESC]),

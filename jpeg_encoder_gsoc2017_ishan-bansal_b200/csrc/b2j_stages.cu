@@ -164,6 +164,29 @@ __global__ void k_rle_words(const int16_t *__restrict__ in, uint32_t *__restrict
     }
 }
 
+// The model's generic run-length code (enc_frame.py:175-176, groupby): one thread per block,
+// (symbol, run) pairs flattened into pairs[b][0 .. counts[b]); at most 64 pairs = 128 values.
+__global__ void k_rle_code(const int16_t *__restrict__ in, int16_t *__restrict__ pairs, int32_t *__restrict__ counts,
+                           long long nblk)
+{
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk) return;
+    const int16_t *c = in + b * 64;
+    int16_t *o = pairs + b * 128;
+    int n = 0, sym = c[0], run = 1;
+    for (int k = 1; k < 64; k++) {
+        const int v = c[k];
+        if (v == sym) { run++; continue; }
+        o[n++] = (int16_t)sym;
+        o[n++] = (int16_t)run;
+        sym = v;
+        run = 1;
+    }
+    o[n++] = (int16_t)sym;
+    o[n++] = (int16_t)run;
+    counts[b] = n;
+}
+
 __global__ void k_entropy_size(const int16_t *__restrict__ in, uint8_t *__restrict__ size, long long n)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -298,6 +321,16 @@ extern "C" int b2j_run_length(const int16_t *in, uint32_t *words, int64_t n_bloc
 extern "C" int b2j_rle_main(const int16_t *in, uint32_t *words, int64_t n_blocks, int32_t prev_dc, void *stream)
 {
     return rle_words(in, words, n_blocks, prev_dc, 1, stream, "b2j_rle_main");
+}
+
+extern "C" int b2j_rle_code(const int16_t *in, int16_t *pairs, int32_t *counts, int64_t n_blocks, void *stream)
+{
+    B2J_REQUIRE(in && pairs && counts, B2J_E_ARG, "b2j_rle_code: null pointer");
+    B2J_REQUIRE(n_blocks >= 0, B2J_E_ARG, "b2j_rle_code: negative size");
+    if (n_blocks == 0) return B2J_OK;
+    k_rle_code<<<(unsigned)((n_blocks + 127) / 128), 128, 0, as_stream(stream)>>>(in, pairs, counts, n_blocks);
+    B2J_LAUNCH_CHECK("k_rle_code");
+    return B2J_OK;
 }
 
 extern "C" int b2j_entropy_size(const int16_t *in, uint8_t *size, int64_t n, void *stream)
