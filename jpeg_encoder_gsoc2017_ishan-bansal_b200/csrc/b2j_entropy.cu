@@ -239,6 +239,9 @@ __global__ void __launch_bounds__(256) k_ff_scan(uint32_t *__restrict__ ffpart, 
 }
 
 
+// grid (x, frames): the CTAs of a frame stride over the chunks the stream really has (the grid is
+// sized from the slot capacity, which is several times the typical stream: empty CTAs cost more
+// than the copy itself).
 __global__ void __launch_bounds__(256) k_stuff_write(const uint8_t *__restrict__ unstuffed, const int64_t *__restrict__ total_bits,
                                                      const uint32_t *__restrict__ ffpart, const int64_t *__restrict__ sizes,
                                                      uint8_t *__restrict__ out, long long ucap, long long out_cap, int chunks,
@@ -246,57 +249,62 @@ __global__ void __launch_bounds__(256) k_stuff_write(const uint8_t *__restrict__
 {
     __shared__ uint32_t s_warp[8];
     __shared__ __align__(16) uint8_t s_out[2 * kStuffChunk + 16];
-    const int f = blockIdx.y, ch = blockIdx.x;
+    const int f = blockIdx.y;
     if (sizes[f] < 0) return;                                       // slot too small: leave it untouched
     const long long nbytes = (total_bits[f] + 7) >> 3;
-    if ((long long)ch * kStuffChunk >= nbytes) return;              // chunk beyond the stream
     uint8_t *dst_frame = out + (long long)f * out_cap;
-    if (ch == 0)
+    if (blockIdx.x == 0)
         for (int i = threadIdx.x; i < kHeaderBytes; i += 256) dst_frame[i] = H.bytes[i];
-    const long long pos = (long long)ch * kStuffChunk + threadIdx.x * 16;
-    uint32_t m = 0;
-    int nvalid = 0;
-    uint4 q = make_uint4(0, 0, 0, 0);
-    if (pos < nbytes) {
-        nvalid = (int)min(16LL, nbytes - pos);
-        q = *reinterpret_cast<const uint4 *>(unstuffed + (long long)f * ucap + pos);
-        m = ff_mask16(q, nvalid);
-    }
-    uint32_t tot;
-    const uint32_t ex = cta_excl_scan_256(__popc(m), s_warp, &tot);
-    // stuffed bytes of this thread into shared memory at its chunk-relative offset
-    {
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-        int o = threadIdx.x * 16 + (int)ex;
+    for (int ch = blockIdx.x; (long long)ch * kStuffChunk < nbytes; ch += gridDim.x) {
+        const long long pos = (long long)ch * kStuffChunk + threadIdx.x * 16;
+        uint32_t m = 0;
+        int nvalid = 0;
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (pos < nbytes) {
+            nvalid = (int)min(16LL, nbytes - pos);
+            q = *reinterpret_cast<const uint4 *>(unstuffed + (long long)f * ucap + pos);
+            m = ff_mask16(q, nvalid);
+        }
+        uint32_t tot;
+        const uint32_t ex = cta_excl_scan_256(__popc(m), s_warp, &tot);
+        // stuffed bytes of this thread into shared memory at its chunk-relative offset
+        {
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            int o = threadIdx.x * 16 + (int)ex;
+            if (tot == 0u && nvalid == 16) {                        // no 0xFF in the whole chunk: plain copy
+                *reinterpret_cast<uint4 *>(s_out + o) = q;
+            } else {
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-            if (i < nvalid) {
-                const uint8_t b = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
-                s_out[o++] = b;
-                if (b == 0xFF) s_out[o++] = 0;
+                for (int i = 0; i < 16; i++) {
+                    if (i < nvalid) {
+                        const uint8_t b = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
+                        s_out[o++] = b;
+                        if (b == 0xFF) s_out[o++] = 0;
+                    }
+                }
             }
         }
-    }
-    __syncthreads();
-    const long long chunk_in = min((long long)kStuffChunk, nbytes - (long long)ch * kStuffChunk);
-    if (chunk_in <= 0) return;
-    const int n_out = (int)chunk_in + (int)tot;
-    uint8_t *dst = dst_frame + kHeaderBytes + (long long)ch * kStuffChunk + ffpart[(long long)f * chunks + ch];
-    // head bytes up to 4-byte alignment, aligned words, tail bytes
-    const int head = min(n_out, (int)((4 - ((uintptr_t)dst & 3)) & 3));
-    if (threadIdx.x < head) dst[threadIdx.x] = s_out[threadIdx.x];
-    const int nwords = (n_out - head) >> 2;
-    uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
-    for (int i = threadIdx.x; i < nwords; i += 256) {
-        const uint8_t *s = s_out + head + 4 * i;
-        dw[i] = (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24);
-    }
-    const int done = head + 4 * nwords;
-    if (threadIdx.x < n_out - done) dst[done + threadIdx.x] = s_out[done + threadIdx.x];
-    // EOI after the last chunk
-    if ((long long)(ch + 1) * kStuffChunk >= nbytes && threadIdx.x == 0) {
-        dst[n_out] = 0xFF;
-        dst[n_out + 1] = 0xD9;
+        __syncthreads();
+        const long long chunk_in = min((long long)kStuffChunk, nbytes - (long long)ch * kStuffChunk);
+        const int n_out = (int)chunk_in + (int)tot;
+        uint8_t *dst = dst_frame + kHeaderBytes + (long long)ch * kStuffChunk + ffpart[(long long)f * chunks + ch];
+        // head bytes up to 4-byte alignment, aligned words, tail bytes
+        const int head = min(n_out, (int)((4 - ((uintptr_t)dst & 3)) & 3));
+        if (threadIdx.x < head) dst[threadIdx.x] = s_out[threadIdx.x];
+        const int nwords = (n_out - head) >> 2;
+        uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
+        for (int i = threadIdx.x; i < nwords; i += 256) {
+            const uint8_t *s = s_out + head + 4 * i;
+            dw[i] = (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24);
+        }
+        const int done = head + 4 * nwords;
+        if (threadIdx.x < n_out - done) dst[done + threadIdx.x] = s_out[done + threadIdx.x];
+        // EOI after the last chunk
+        if ((long long)(ch + 1) * kStuffChunk >= nbytes && threadIdx.x == 0) {
+            dst[n_out] = 0xFF;
+            dst[n_out + 1] = 0xD9;
+        }
+        __syncthreads();                                            // s_out and s_warp are reused by the next chunk
     }
 }
 
@@ -314,7 +322,12 @@ int launch_stuffing(const uint8_t *unstuffed, const int64_t *total_bits, uint32_
     }
     k_ff_scan<<<(unsigned)n_frames, 256, 0, st>>>(ffpart, total_bits, sizes, ucap, out_cap, schunks, kHeaderBytes, error_flag);
     B2J_LAUNCH_CHECK("k_ff_scan");
-    k_stuff_write<<<sgrid, 256, 0, st>>>(unstuffed, total_bits, ffpart, sizes, out, ucap, out_cap, schunks, H);
+    // enough CTAs per frame to fill the GPU a few times over, never more than the slot has chunks
+    int per_frame = (148 * 16 + n_frames - 1) / n_frames;
+    if (per_frame > schunks) per_frame = schunks;
+    if (per_frame < 1) per_frame = 1;
+    k_stuff_write<<<dim3((unsigned)per_frame, (unsigned)n_frames), 256, 0, st>>>(unstuffed, total_bits, ffpart, sizes, out, ucap,
+                                                                                 out_cap, schunks, H);
     B2J_LAUNCH_CHECK("k_stuff_write");
     return B2J_OK;
 }
