@@ -65,6 +65,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=None, help="frames per GPU (default: the named workload)")
     ap.add_argument("--config", default="2", choices=sorted(PRESETS), help="BASELINE.json config (default 2, the headline)")
+    ap.add_argument("--dct", default="model", choices=["model", "fixed"],
+                    help="model = float64 model arithmetic (parity path, the headline); fixed = [ext] gateware fixed point, non-parity")
     ap.add_argument("--kind", default="photo", choices=["photo", "noise", "grey"], help="synthetic content (SURVEY 8d stress)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
@@ -77,6 +79,8 @@ def parse():
     UNIQUE_FRAMES = max(1, min(UNIQUE_FRAMES, (32 * 1080 * 1920) // (H * W)))     # bound the host-side generation time
     if KIND != "photo":
         WORKLOAD += " [content: %s]" % KIND
+    if args.dct != "model":
+        WORKLOAD += " [dct: %s, NON-PARITY arithmetic mode]" % args.dct
     return args
 
 
@@ -260,6 +264,7 @@ def main():
     qy, qc = lj.quant_tables(QUALITY)
     qy_a, qc_a = lj._lib.table_arg(qy), lj._lib.table_arg(qc)
     zrl = lj._lib.ZRL[ZRL]
+    dct_flag = lj._lib.DCT_MODE[args.dct]
     cap = int(L.b2j_default_out_cap(ctypes.byref(desc)))
     nblk = frames * geo.blocks_per_frame
     coefs = torch.empty((nblk, 64), dtype=torch.int16, device=dev)
@@ -274,7 +279,7 @@ def main():
     def step(ev=None):
         """One pass of the hot path: exactly the launches b2j_encode issues, with optional stage events."""
         if ev: ev[0].record(stream)
-        lj._lib.check(L.b2j_fused_block(rgb.data_ptr(), dref, qy_a, qc_a, coefs.data_ptr(), 0, sp))
+        lj._lib.check(L.b2j_fused_block(rgb.data_ptr(), dref, qy_a, qc_a, coefs.data_ptr(), dct_flag, sp))
         if ev: ev[1].record(stream)
         lj._lib.check(L.b2j_entropy_encode(coefs.data_ptr(), dref, qy_a, qc_a, zrl, ent_ptr, out.data_ptr(), cap,
                                            sizes.data_ptr(), sp))
@@ -290,7 +295,7 @@ def main():
     torch.cuda.synchronize()
     sz = sizes.cpu()
     assert int(sz.min()) > 0, "a frame did not fit its output slot"
-    enc = lj.JpegEncoder(SUB, quality=QUALITY, zrl=ZRL)
+    enc = lj.JpegEncoder(SUB, quality=QUALITY, zrl=ZRL, dct=args.dct)
     out2, sz2 = enc.encode_device(rgb)
     torch.cuda.synchronize()
     assert torch.equal(sz2.cpu(), sz) and torch.equal(out2[0, :int(sz[0])], out[0, :int(sz[0])])
@@ -328,7 +333,7 @@ def main():
     if not args.skip_e2e:
         out_host = torch.empty((frames, cap), dtype=torch.uint8).pin_memory()
         sizes_host = torch.empty((frames,), dtype=torch.int64)
-        henc = lj.JpegEncoder(SUB, quality=QUALITY, zrl=ZRL, out_cap=cap)
+        henc = lj.JpegEncoder(SUB, quality=QUALITY, zrl=ZRL, out_cap=cap, dct=args.dct)
         fpc = max(1, 16 * 1080 * 1920 // (H * W))
         for _ in range(2):
             henc.encode_host(host, out_host, sizes_host, frames_per_chunk=fpc)
@@ -373,13 +378,14 @@ def main():
     k1_ms = stage_ms[0]
     achieved = k1_bytes / (k1_ms / 1e3) / 1e9
     traffic = None
-    if args.config == "2" and KIND == "photo" and frames == FRAMES_PER_GPU:      # the capture was taken on this workload
+    if args.config == "2" and KIND == "photo" and frames == FRAMES_PER_GPU and args.dct == "model":   # the capture's workload
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
         except Exception:
             pass
     hv = {"444": "1,1", "422": "2,1", "420": "2,2"}[SUB]
-    roofline = {"kernel": "k_fused_tiled<%s> (K1: colour + chroma resampling + float64 DCT + quantise + zig-zag)" % hv,
+    roofline = {"kernel": "k_fused_tiled<%s> (K1: colour + chroma resampling + %s DCT + quantise + zig-zag)"
+                          % (hv, "float64" if args.dct == "model" else "fixed-point"),
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "frac_of_nominal_8000": achieved / 8000.0,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
@@ -391,7 +397,7 @@ def main():
                         "other instructions per 8x8 block-equivalent (DESIGN.md)"}
 
     base = None
-    if not args.skip_cpu_baseline and n_gpus == 1:        # reported on rank 0 at N = 1 only
+    if not args.skip_cpu_baseline and n_gpus == 1 and args.dct == "model":        # reported on rank 0 at N = 1 only
         base, _ = cpu_baseline(host, 1)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,

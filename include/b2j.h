@@ -59,6 +59,14 @@ extern "C" {
 #define B2J_FUSED_AUTO 0    /* tiled kernel when the layout allows, else simple */
 #define B2J_FUSED_SIMPLE 1  /* one thread per 8x8 block, any geometry */
 #define B2J_FUSED_TILED 2   /* shared-memory tiled, bulk-async loads; needs 16-byte aligned rows */
+/* OR-ed into `variant`: [ext] DCT in the gateware's fixed-point arithmetic
+ * (litejpeg/core/new_dct6.py:171-396: its constants and shift points, the two
+ * wiring slips :262-263 / :294 corrected, 32-bit sums) instead of the float64
+ * model.  NOT parity with the model (<= 4 LSB per coefficient before
+ * quantisation); checked against its own restatement oracle/gateware.py. */
+#define B2J_FUSED_DCT_FIXED 0x100
+/* the same choice for b2j_encode / b2j_encoder_create, OR-ed into `zrl` */
+#define B2J_OPT_DCT_FIXED 0x100
 
 /* A batch of equally sized, interleaved 8-bit RGB frames (H x W x 3, like the
  * array the model reads at test/model/enc_frame.py:7-10). */
@@ -124,6 +132,10 @@ int b2j_chroma_subsample(const uint8_t *in, uint8_t *out, int32_t height, int32_
  * arithmetic of dct, test/model/enc_frame.py:42-109 (float64 graph, int(v/8)).
  * in: n_blocks x 64 samples 0..255, row-major; out: n_blocks x 64, [v][u]. */
 int b2j_dct(const int16_t *in, int16_t *out, int64_t n_blocks, void *stream);
+
+/* [ext] DCT stage in the gateware's fixed-point arithmetic: DCTDatapath,
+ * litejpeg/core/new_dct6.py:107-145 and dct1D :171-396 (see B2J_FUSED_DCT_FIXED). */
+int b2j_dct_fixed(const int16_t *in, int16_t *out, int64_t n_blocks, void *stream);
 
 /* replaces: Quantization, litejpeg/core/quantization.py:29-182 and quantize,
  * test/model/enc_frame.py:111-129. */
@@ -202,7 +214,7 @@ int b2j_entropy_encode(const int16_t *coefs, const b2j_image_desc *desc,
 
 /* The whole path K1..K4 on device buffers.  workspace: b2j_encode_workspace_bytes().
  * quality 1..100 picks the [ext] IJG tables, or pass quality = 0 and explicit
- * tables. */
+ * tables.  zrl: B2J_ZRL_*, optionally | B2J_OPT_DCT_FIXED. */
 size_t b2j_encode_workspace_bytes(const b2j_image_desc *desc, int64_t out_cap);
 int64_t b2j_default_out_cap(const b2j_image_desc *desc);
 int b2j_encode(const uint8_t *rgb, const b2j_image_desc *desc, int quality,

@@ -55,6 +55,7 @@ SIGNATURES = {
     "b2j_entropy_size": (c_int, [_P, _P, c_int64, _P]),
     "b2j_rle_main": (c_int, [_P, _P, c_int64, c_int32, _P]),
     "b2j_rle_code": (c_int, [_P, _P, _P, c_int64, _P]),
+    "b2j_dct_fixed": (c_int, [_P, _P, c_int64, _P]),
     "b2j_fused_block": (c_int, [_P, _DESC, _P, _P, _P, c_int, _P]),
     "b2j_block_bits": (c_int, [_P, _DESC, c_int, _P, _P]),
     "b2j_scan_workspace_bytes": (c_size_t, [_DESC]),
@@ -77,6 +78,7 @@ SUB = {"444": 444, "422": 422, "420": 420}
 ZRL = {"eager": 0, "standard": 1}
 CSC = {"jfif": 0, "xapp930": 1}
 QMODE = {"round": 0, "trunc": 1, "reciprocal": 2}
+DCT_MODE = {"model": 0, "fixed": 0x100}      # B2J_FUSED_DCT_FIXED / B2J_OPT_DCT_FIXED
 FUSED = {"auto": 0, "simple": 1, "tiled": 2}
 
 _lib = None

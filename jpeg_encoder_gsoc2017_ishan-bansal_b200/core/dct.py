@@ -15,9 +15,15 @@ datapath_latency = 8      # new_dct6.py:20
 
 
 class DCT:
-    def __init__(self, dw=12, dct_block=64):
+    def __init__(self, dw=12, dct_block=64, mode="model"):
+        """mode="model": the float64 software model (enc_frame.py:38-109), the parity path.
+        mode="fixed": [ext] the gateware datapath's fixed-point arithmetic (new_dct6.py:171-396,
+        its two wiring slips corrected, wide sums); <= 4 LSB from the model, not parity."""
         if dct_block != 64:
             raise ValueError("dct_block must be 64")
+        if mode not in _lib.DCT_MODE:
+            raise ValueError("mode must be 'model' or 'fixed'")
+        self.mode = mode
         self.dw = dw
         self.sink_layout = block_layout(dw)
         self.source_layout = block_layout(dw)
@@ -34,7 +40,8 @@ class DCT:
             raise ValueError("DCT input must be a multiple of 64 words")
         out = torch.empty_like(t)
         with torch.cuda.device(t.device):
-            _lib.check(_lib.lib().b2j_dct(t.data_ptr(), out.data_ptr(), t.numel() // 64, stream_ptr(stream)))
+            fn = _lib.lib().b2j_dct_fixed if self.mode == "fixed" else _lib.lib().b2j_dct
+            _lib.check(fn(t.data_ptr(), out.data_ptr(), t.numel() // 64, stream_ptr(stream)))
         if packet:
             return to_unsigned(out.cpu().tolist(), self.dw)
         return out

@@ -75,8 +75,10 @@ extern "C" int b2j_encode(const uint8_t *rgb, const b2j_image_desc *desc, int qu
     B2J_REQUIRE(workspace_bytes >= w.total, B2J_E_WORKSPACE, "b2j_encode: workspace %zu < %zu bytes", workspace_bytes, w.total);
     uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
     int16_t *coefs = reinterpret_cast<int16_t *>(ws + w.coefs);
-    if ((rc = b2j_fused_block(rgb, desc, qy, qc, coefs, B2J_FUSED_AUTO, stream))) return rc;
-    if ((rc = b2j_entropy_encode(coefs, desc, qy, qc, zrl, ws + w.entropy_ws, out, out_cap, sizes, stream))) return rc;
+    const int variant = B2J_FUSED_AUTO | ((zrl & B2J_OPT_DCT_FIXED) ? B2J_FUSED_DCT_FIXED : 0);
+    if ((rc = b2j_fused_block(rgb, desc, qy, qc, coefs, variant, stream))) return rc;
+    if ((rc = b2j_entropy_encode(coefs, desc, qy, qc, zrl & ~B2J_OPT_DCT_FIXED, ws + w.entropy_ws, out, out_cap, sizes, stream)))
+        return rc;
     return B2J_OK;
 }
 
@@ -117,7 +119,8 @@ extern "C" int b2j_encoder_create(b2j_encoder **enc, const b2j_image_desc *desc,
 {
     B2J_REQUIRE(enc && desc, B2J_E_ARG, "b2j_encoder_create: null pointer");
     B2J_REQUIRE(quality >= 1 && quality <= 100, B2J_E_ARG, "b2j_encoder_create: quality %d not in 1..100", quality);
-    B2J_REQUIRE(zrl == B2J_ZRL_EAGER || zrl == B2J_ZRL_STANDARD, B2J_E_ARG, "b2j_encoder_create: bad zrl policy");
+    B2J_REQUIRE((zrl & ~B2J_OPT_DCT_FIXED) == B2J_ZRL_EAGER || (zrl & ~B2J_OPT_DCT_FIXED) == B2J_ZRL_STANDARD, B2J_E_ARG,
+                "b2j_encoder_create: bad zrl policy");
     B2J_REQUIRE(frames_per_chunk >= 1, B2J_E_ARG, "b2j_encoder_create: frames_per_chunk must be >= 1");
     B2J_REQUIRE(desc->row_stride == 0 && desc->frame_stride == 0, B2J_E_ARG, "b2j_encoder_create: host frames must be packed");
     b2j_image_desc d = *desc;

@@ -124,6 +124,41 @@ __device__ __forceinline__ void dct_quant_block(const uint2 (&px)[8], P &p)
     dct_1d(m7); emit_col_d<7>(m7, p);
 }
 
+// [ext] the same block in the gateware's fixed-point arithmetic (b2j_math.cuh dct_1d_fixed):
+// rows, columns, arithmetic >> 3 (new_dct6.py:107-140), then the model's quantiser.
+template <int U, class P>
+__device__ __forceinline__ void emit_col_fixed(const int (&c)[8], P &p)
+{
+#define B2J_EMITF(VV) do { const int o_ = c[VV] >> 3; p.template put<VV * 8 + U>((uint32_t)abs(o_), o_ < 0); } while (0)
+    B2J_EMITF(0); B2J_EMITF(1); B2J_EMITF(2); B2J_EMITF(3); B2J_EMITF(4); B2J_EMITF(5); B2J_EMITF(6); B2J_EMITF(7);
+#undef B2J_EMITF
+}
+
+template <class P>
+__device__ __forceinline__ void dct_quant_block_fixed(const uint2 (&px)[8], P &p)
+{
+    int m[8][8];                   // m[u][x]: row-pass output u of row x
+#pragma unroll
+    for (int x = 0; x < 8; x++) {
+        int s[8];
+        s[0] = (int)__byte_perm(px[x].x, 0u, 0x4440) - 128; s[1] = (int)__byte_perm(px[x].x, 0u, 0x4441) - 128;
+        s[2] = (int)__byte_perm(px[x].x, 0u, 0x4442) - 128; s[3] = (int)__byte_perm(px[x].x, 0u, 0x4443) - 128;
+        s[4] = (int)__byte_perm(px[x].y, 0u, 0x4440) - 128; s[5] = (int)__byte_perm(px[x].y, 0u, 0x4441) - 128;
+        s[6] = (int)__byte_perm(px[x].y, 0u, 0x4442) - 128; s[7] = (int)__byte_perm(px[x].y, 0u, 0x4443) - 128;
+        dct_1d_fixed(s);
+#pragma unroll
+        for (int u = 0; u < 8; u++) m[u][x] = s[u];
+    }
+    dct_1d_fixed(m[0]); emit_col_fixed<0>(m[0], p);
+    dct_1d_fixed(m[1]); emit_col_fixed<1>(m[1], p);
+    dct_1d_fixed(m[2]); emit_col_fixed<2>(m[2], p);
+    dct_1d_fixed(m[3]); emit_col_fixed<3>(m[3], p);
+    dct_1d_fixed(m[4]); emit_col_fixed<4>(m[4], p);
+    dct_1d_fixed(m[5]); emit_col_fixed<5>(m[5], p);
+    dct_1d_fixed(m[6]); emit_col_fixed<6>(m[6], p);
+    dct_1d_fixed(m[7]); emit_col_fixed<7>(m[7], p);
+}
+
 struct FusedParams {
     const uint8_t *rgb;
     int16_t *coefs;
@@ -136,7 +171,7 @@ struct FusedParams {
 };
 
 // =============================================================== simple variant
-template <int H, int V>
+template <int H, int V, bool FIXED>
 __global__ void __launch_bounds__(128) k_fused_simple(const __grid_constant__ FusedParams P)
 {
     constexpr int BPM = H * V + 2;
@@ -183,7 +218,8 @@ __global__ void __launch_bounds__(128) k_fused_simple(const __grid_constant__ Fu
     }
     BlockPacker pk;
     pk.init(s_mul[comp ? 1 : 0]);
-    dct_quant_block(px, pk);
+    if (FIXED) dct_quant_block_fixed(px, pk);
+    else dct_quant_block(px, pk);
     pk.store(P.coefs + gb * 64);
 }
 
@@ -262,7 +298,7 @@ __device__ __forceinline__ TileCoord tile_coord(const FusedParams &P, long long 
     return c;
 }
 
-template <int H, int V>
+template <int H, int V, bool FIXED>
 __global__ void __launch_bounds__(kThreads, B2J_K1_MIN_CTAS) k_fused_tiled(const __grid_constant__ FusedParams P, long long n_tiles, int tiles_x)
 {
     using TS = TileShape<H, V>;
@@ -476,7 +512,8 @@ __global__ void __launch_bounds__(kThreads, B2J_K1_MIN_CTAS) k_fused_tiled(const
                     for (int i = 0; i < 8; i++) px[i] = *reinterpret_cast<const uint2 *>(plane + i * pitch + bx * 8);
                     BlockPacker pk;
                     pk.init(mul);
-                    dct_quant_block(px, pk);
+                    if (FIXED) dct_quant_block_fixed(px, pk);
+                    else dct_quant_block(px, pk);
                     pk.store(P.coefs + (mcu * BPM + k) * 64);
                 }
             }
@@ -487,12 +524,12 @@ __global__ void __launch_bounds__(kThreads, B2J_K1_MIN_CTAS) k_fused_tiled(const
     }
 }
 
-template <int H, int V>
+template <int H, int V, bool FIXED>
 static int launch_fused(const FusedParams &P, const Geo &g, int variant, cudaStream_t st)
 {
     if (variant == B2J_FUSED_SIMPLE) {
         const long long nblk = (long long)g.n_frames * g.blocks_per_frame;
-        k_fused_simple<H, V><<<(unsigned)((nblk + 127) / 128), 128, 0, st>>>(P);
+        k_fused_simple<H, V, FIXED><<<(unsigned)((nblk + 127) / 128), 128, 0, st>>>(P);
         B2J_LAUNCH_CHECK("k_fused_simple");
         return B2J_OK;
     }
@@ -502,9 +539,9 @@ static int launch_fused(const FusedParams &P, const Geo &g, int variant, cudaStr
     int dev = 0, sms = 148;
     B2J_CUDA(cudaGetDevice(&dev));
     B2J_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    B2J_CUDA(cudaFuncSetAttribute(k_fused_tiled<H, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS::kSmem));
+    B2J_CUDA(cudaFuncSetAttribute(k_fused_tiled<H, V, FIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS::kSmem));
     int per_sm = 2;
-    B2J_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_tiled<H, V>, kThreads, TS::kSmem));
+    B2J_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_tiled<H, V, FIXED>, kThreads, TS::kSmem));
 #ifdef B2J_K1_MAX_CTAS
     if (per_sm > B2J_K1_MAX_CTAS) per_sm = B2J_K1_MAX_CTAS;
 #endif
@@ -514,7 +551,7 @@ static int launch_fused(const FusedParams &P, const Geo &g, int variant, cudaStr
     }
     if (per_sm < 1) per_sm = 1;
     const long long grid = n_tiles < (long long)per_sm * sms ? n_tiles : (long long)per_sm * sms;   // persistent CTAs
-    k_fused_tiled<H, V><<<(unsigned)grid, kThreads, TS::kSmem, st>>>(P, n_tiles, tiles_x);
+    k_fused_tiled<H, V, FIXED><<<(unsigned)grid, kThreads, TS::kSmem, st>>>(P, n_tiles, tiles_x);
     B2J_LAUNCH_CHECK("k_fused_tiled");
     return B2J_OK;
 }
@@ -527,6 +564,8 @@ extern "C" int b2j_fused_block(const uint8_t *rgb, const b2j_image_desc *desc, c
                                const uint8_t qc_host[64], int16_t *coefs, int variant, void *stream)
 {
     B2J_REQUIRE(rgb && coefs && qy_host && qc_host, B2J_E_ARG, "b2j_fused_block: null pointer");
+    const bool fixed = (variant & B2J_FUSED_DCT_FIXED) != 0;
+    variant &= ~B2J_FUSED_DCT_FIXED;
     B2J_REQUIRE(variant >= B2J_FUSED_AUTO && variant <= B2J_FUSED_TILED, B2J_E_ARG, "b2j_fused_block: bad variant %d", variant);
     B2J_REQUIRE(((uintptr_t)coefs & 15) == 0, B2J_E_ALIGN, "b2j_fused_block: coefs must be 16-byte aligned");
     Geo g;
@@ -542,7 +581,12 @@ extern "C" int b2j_fused_block(const uint8_t *rgb, const b2j_image_desc *desc, c
     make_quant_mul(qy_host, qc_host, &P.qm);
     cudaStream_t st = as_stream(stream);
     if (variant == B2J_FUSED_AUTO) variant = B2J_FUSED_TILED;
-    if (g.h == 1) return launch_fused<1, 1>(P, g, variant, st);
-    if (g.v == 1) return launch_fused<2, 1>(P, g, variant, st);
-    return launch_fused<2, 2>(P, g, variant, st);
+    if (fixed) {
+        if (g.h == 1) return launch_fused<1, 1, true>(P, g, variant, st);
+        if (g.v == 1) return launch_fused<2, 1, true>(P, g, variant, st);
+        return launch_fused<2, 2, true>(P, g, variant, st);
+    }
+    if (g.h == 1) return launch_fused<1, 1, false>(P, g, variant, st);
+    if (g.v == 1) return launch_fused<2, 1, false>(P, g, variant, st);
+    return launch_fused<2, 2, false>(P, g, variant, st);
 }

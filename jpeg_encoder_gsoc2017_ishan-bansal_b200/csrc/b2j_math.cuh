@@ -204,6 +204,65 @@ __device__ __forceinline__ void dct_1d_int(const int (&x)[8], int &r0, int &r4,
     r3 = __dmul_rn(B2J_SQRT2, e5);
 }
 
+// [ext] "fixed" DCT mode: one pass of the gateware datapath
+// litejpeg/core/new_dct6.py:171-396 - its constants and shift points (:219-230, :345, :370),
+// every product floor(c * x / 2^s) - with the two wiring slips of the source (:262-263, :294)
+// corrected so that the graph is the model's, and 32-bit sums instead of wrapping 12-bit ones.
+// Not parity with the float64 model (<= 4 LSB away); oracle: oracle/gateware.py dct_1d_fixed.
+__device__ __forceinline__ void dct_1d_fixed(int (&v)[8])
+{
+#define B2J_BF(i, j) do { const int a_ = v[i] + v[j], b_ = v[i] - v[j]; v[i] = a_; v[j] = b_; } while (0)
+    B2J_BF(3, 4); B2J_BF(2, 5); B2J_BF(1, 6); B2J_BF(0, 7);
+    B2J_BF(0, 3); B2J_BF(1, 2);
+    {
+        const int v4 = v[4], v7 = v[7], v5 = v[5], v6 = v[6];
+        v[4] = ((213 * v4) >> 8) + ((569 * v7) >> 10);
+        v[7] = ((213 * v7) >> 8) - ((569 * v4) >> 10);
+        v[5] = ((1004 * v5) >> 10) + ((25 * v6) >> 7);
+        v[6] = ((1004 * v6) >> 10) - ((25 * v5) >> 7);
+    }
+    B2J_BF(7, 5); B2J_BF(4, 6); B2J_BF(0, 1);
+    {
+        const int fa = ((49 * v[2]) >> 7) + ((473 * v[3]) >> 9);
+        const int fs = ((49 * v[3]) >> 7) - ((473 * v[2]) >> 9);
+        v[2] = (181 * fa) >> 7;
+        v[3] = (181 * fs) >> 7;
+    }
+    const int r1 = v[7] + v[4], r7 = v[7] - v[4];
+    const int r5 = (181 * v[6]) >> 7, r3 = (181 * v[5]) >> 7;
+    const int r6 = v[3], r2 = v[2], r4 = v[1], r0 = v[0];
+    v[0] = r0; v[1] = r1; v[2] = r2; v[3] = r3; v[4] = r4; v[5] = r5; v[6] = r6; v[7] = r7;
+#undef B2J_BF
+}
+
+// new_dct6.py:107-145 with dct_1d_fixed: -128, rows, columns, arithmetic >> 3.
+// Emit(natural_index, |coefficient|, negative?) like dct_block below.
+template <class Emit>
+__device__ __forceinline__ void dct_block_fixed(const uint2 (&px)[8], Emit &&emit)
+{
+    int m[8][8];
+#pragma unroll
+    for (int x = 0; x < 8; x++) {
+        int s[8];
+        s[0] = (int)__byte_perm(px[x].x, 0u, 0x4440) - 128; s[1] = (int)__byte_perm(px[x].x, 0u, 0x4441) - 128;
+        s[2] = (int)__byte_perm(px[x].x, 0u, 0x4442) - 128; s[3] = (int)__byte_perm(px[x].x, 0u, 0x4443) - 128;
+        s[4] = (int)__byte_perm(px[x].y, 0u, 0x4440) - 128; s[5] = (int)__byte_perm(px[x].y, 0u, 0x4441) - 128;
+        s[6] = (int)__byte_perm(px[x].y, 0u, 0x4442) - 128; s[7] = (int)__byte_perm(px[x].y, 0u, 0x4443) - 128;
+        dct_1d_fixed(s);
+#pragma unroll
+        for (int u = 0; u < 8; u++) m[u][x] = s[u];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        dct_1d_fixed(m[u]);
+#pragma unroll
+        for (int vv = 0; vv < 8; vv++) {
+            const int o = m[u][vv] >> 3;
+            emit(vv * 8 + u, (uint32_t)abs(o), o < 0);
+        }
+    }
+}
+
 // One 8x8 block held by one thread.  px[row] = the 8 samples of a row as two
 // little-endian words.  Emit(natural_index, magnitude of int(v/8), negative?)
 // is called for all 64 coefficients.

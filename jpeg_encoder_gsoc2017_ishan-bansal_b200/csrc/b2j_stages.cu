@@ -113,6 +113,27 @@ __global__ void __launch_bounds__(128) k_dct(const int16_t *__restrict__ in, int
     dct_block(px, [&](int idx, uint32_t mag, bool neg) { o[idx] = (int16_t)(neg ? -(int)mag : (int)mag); });
 }
 
+// [ext] the gateware's fixed-point arithmetic (new_dct6.py:171-396, corrected; b2j_math.cuh)
+__global__ void __launch_bounds__(128) k_dct_fixed(const int16_t *__restrict__ in, int16_t *__restrict__ out, long long nblk)
+{
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk) return;
+    const int16_t *p = in + b * 64;
+    uint2 px[8];
+#pragma unroll
+    for (int x = 0; x < 8; x++) {
+        uint32_t w0 = 0, w1 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            w0 |= ((uint32_t)p[x * 8 + k] & 0xFFu) << (8 * k);
+            w1 |= ((uint32_t)p[x * 8 + 4 + k] & 0xFFu) << (8 * k);
+        }
+        px[x] = make_uint2(w0, w1);
+    }
+    int16_t *o = out + b * 64;
+    dct_block_fixed(px, [&](int idx, uint32_t mag, bool neg) { o[idx] = (int16_t)(neg ? -(int)mag : (int)mag); });
+}
+
 // ---- Quantization (litejpeg/core/quantization.py:29-182; model enc_frame.py:111-129)
 struct QTable { uint8_t q[64]; };
 __global__ void k_quantize(const int16_t *__restrict__ in, int16_t *__restrict__ out, long long n, QTable t, int mode)
@@ -272,6 +293,16 @@ extern "C" int b2j_dct(const int16_t *in, int16_t *out, int64_t n_blocks, void *
     if (n_blocks == 0) return B2J_OK;
     k_dct<<<(unsigned)((n_blocks + 127) / 128), 128, 0, as_stream(stream)>>>(in, out, n_blocks);
     B2J_LAUNCH_CHECK("k_dct");
+    return B2J_OK;
+}
+
+extern "C" int b2j_dct_fixed(const int16_t *in, int16_t *out, int64_t n_blocks, void *stream)
+{
+    B2J_REQUIRE(in && out, B2J_E_ARG, "b2j_dct_fixed: null pointer");
+    B2J_REQUIRE(n_blocks >= 0, B2J_E_ARG, "b2j_dct_fixed: negative size");
+    if (n_blocks == 0) return B2J_OK;
+    k_dct_fixed<<<(unsigned)((n_blocks + 127) / 128), 128, 0, as_stream(stream)>>>(in, out, n_blocks);
+    B2J_LAUNCH_CHECK("k_dct_fixed");
     return B2J_OK;
 }
 

@@ -29,15 +29,20 @@ class JpegEncoder:
     subsampling: "444" | "422" | "420"; quality: 1..100 ([ext] IJG scaling; 85
     reproduces the model's tables enc_frame.py:141-159) or explicit `tables=(qy, qc)`;
     zrl: "eager" (gateware run-length rule, rlecore.py:101-105) | "standard".
+    dct: "model" (float64 model, the parity path) | "fixed" ([ext] the gateware's fixed-point DCT
+    arithmetic, new_dct6.py:171-396 corrected; <= 4 LSB per coefficient from the model, not parity).
     """
 
-    def __init__(self, subsampling="444", quality=85, zrl="eager", tables=None, out_cap=None):
+    def __init__(self, subsampling="444", quality=85, zrl="eager", tables=None, out_cap=None, dct="model"):
         if str(subsampling) not in _lib.SUB:
             raise ValueError("subsampling must be '444', '422' or '420'")
         if zrl not in _lib.ZRL:
             raise ValueError("zrl must be 'eager' or 'standard'")
+        if dct not in _lib.DCT_MODE:
+            raise ValueError("dct must be 'model' (float64 model, the parity path) or 'fixed' ([ext] gateware arithmetic)")
         self.subsampling = str(subsampling)
         self.zrl = zrl
+        self.dct = dct
         if tables is not None:
             self.quality = 0
             self.qy, self.qc = [int(v) for v in tables[0]], [int(v) for v in tables[1]]
@@ -89,8 +94,8 @@ class JpegEncoder:
         coefs = torch.empty((desc.n_frames, g.blocks_per_frame, 64), dtype=torch.int16, device=rgb.device)
         with torch.cuda.device(rgb.device):
             _lib.check(_lib.lib().b2j_fused_block(rgb.data_ptr(), ctypes.byref(desc), _lib.table_arg(self.qy),
-                                                   _lib.table_arg(self.qc), coefs.data_ptr(), _lib.FUSED[variant],
-                                                   stream_ptr(stream)))
+                                                   _lib.table_arg(self.qc), coefs.data_ptr(),
+                                                   _lib.FUSED[variant] | _lib.DCT_MODE[self.dct], stream_ptr(stream)))
         return coefs
 
     def encode_device(self, rgb, out=None, sizes=None, stream=None):
@@ -108,7 +113,8 @@ class JpegEncoder:
             sizes = torch.empty((desc.n_frames,), dtype=torch.int64, device=rgb.device)
         with torch.cuda.device(rgb.device):
             _lib.check(_lib.lib().b2j_encode(rgb.data_ptr(), ctypes.byref(desc), self.quality, _lib.table_arg(self.qy),
-                                              _lib.table_arg(self.qc), _lib.ZRL[self.zrl], ws.data_ptr(), ws.numel(),
+                                              _lib.table_arg(self.qc), _lib.ZRL[self.zrl] | _lib.DCT_MODE[self.dct], ws.data_ptr(),
+                                              ws.numel(),
                                               out.data_ptr(), cap, sizes.data_ptr(), stream_ptr(stream)))
         return out, sizes
 
@@ -146,7 +152,7 @@ class JpegEncoder:
             d1 = _lib.make_desc(desc.height, desc.width, self.subsampling, fpc)
             if self.quality == 0:
                 raise ValueError("encode_host needs a quality (explicit tables are not supported on this path)")
-            _lib.check(_lib.lib().b2j_encoder_create(ctypes.byref(handle), ctypes.byref(d1), self.quality, _lib.ZRL[self.zrl],
+            _lib.check(_lib.lib().b2j_encoder_create(ctypes.byref(handle), ctypes.byref(d1), self.quality, _lib.ZRL[self.zrl] | _lib.DCT_MODE[self.dct],
                                                       cap, fpc))
             enc = handle
             self._host = {key: enc}

@@ -92,6 +92,54 @@ static void dct_block(const int *in, int *out)
     }
 }
 
+/* [ext] "fixed" DCT mode: litejpeg/core/new_dct6.py:171-396 with its own constants and shift points,
+ * the two wiring slips (:262-263, :294) corrected and wide sums; see oracle/gateware.py dct_1d_fixed.
+ * `>>` on negative ints is an arithmetic shift with gcc (floor), as in the gateware. */
+static void dct_1d_fixed(int *v)
+{
+    int a, b;
+#define BF(i, j) do { a = v[i] + v[j]; b = v[i] - v[j]; v[i] = a; v[j] = b; } while (0)
+    BF(3, 4); BF(2, 5); BF(1, 6); BF(0, 7);
+    BF(0, 3); BF(1, 2);
+    {
+        const int v4 = v[4], v7 = v[7], v5 = v[5], v6 = v[6];
+        v[4] = ((213 * v4) >> 8) + ((569 * v7) >> 10);
+        v[7] = ((213 * v7) >> 8) - ((569 * v4) >> 10);
+        v[5] = ((1004 * v5) >> 10) + ((25 * v6) >> 7);
+        v[6] = ((1004 * v6) >> 10) - ((25 * v5) >> 7);
+    }
+    BF(7, 5); BF(4, 6); BF(0, 1);
+    {
+        const int fa = ((49 * v[2]) >> 7) + ((473 * v[3]) >> 9);
+        const int fs = ((49 * v[3]) >> 7) - ((473 * v[2]) >> 9);
+        v[2] = (181 * fa) >> 7; v[3] = (181 * fs) >> 7;
+    }
+    {
+        int r[8];
+        r[1] = v[7] + v[4]; r[7] = v[7] - v[4];
+        r[5] = (181 * v[6]) >> 7; r[3] = (181 * v[5]) >> 7;
+        r[6] = v[3]; r[2] = v[2]; r[4] = v[1]; r[0] = v[0];
+        memcpy(v, r, sizeof r);
+    }
+#undef BF
+}
+
+/* new_dct6.py:107-145: -128, rows, columns, arithmetic >> 3 */
+static void dct_block_fixed(const int *in, int *out)
+{
+    int m[64], vec[8];
+    for (int x = 0; x < 8; x++) {
+        for (int y = 0; y < 8; y++) vec[y] = in[x * 8 + y] - 128;
+        dct_1d_fixed(vec);
+        for (int y = 0; y < 8; y++) m[x * 8 + y] = vec[y];
+    }
+    for (int y = 0; y < 8; y++) {
+        for (int x = 0; x < 8; x++) vec[x] = m[x * 8 + y];
+        dct_1d_fixed(vec);
+        for (int x = 0; x < 8; x++) out[x * 8 + y] = vec[x] >> 3;
+    }
+}
+
 /* enc_frame.py:111-129 == sign(v) * ((2|v| + d) / (2d)) */
 static inline int quant1(int v, int d)
 {
@@ -113,6 +161,12 @@ int b2jo_rgb2ycbcr(const uint8_t *rgb, int64_t npx, uint8_t *y, uint8_t *cb, uin
 int b2jo_dct(const int32_t *in, int64_t nblk, int32_t *out)
 {
     for (int64_t i = 0; i < nblk; i++) dct_block(in + 64 * i, out + 64 * i);
+    return 0;
+}
+
+int b2jo_dct_fixed(const int32_t *in, int64_t nblk, int32_t *out)
+{
+    for (int64_t i = 0; i < nblk; i++) dct_block_fixed(in + 64 * i, out + 64 * i);
     return 0;
 }
 
@@ -163,8 +217,17 @@ static int make_geo(int height, int width, int sub, geo_t *g)
 
 /* RGB (H, W, 3) -> zig-zag quantised coefficients, scan (MCU) order,
  * [n_mcu][bpm][64] int16, DC not differenced. */
+int b2jo_encode_coefficients_ex(const uint8_t *rgb, int height, int width, int sub,
+                                const uint8_t *qy, const uint8_t *qc, int dct_fixed, int16_t *coefs);
 int b2jo_encode_coefficients(const uint8_t *rgb, int height, int width, int sub,
                              const uint8_t *qy, const uint8_t *qc, int16_t *coefs)
+{
+    return b2jo_encode_coefficients_ex(rgb, height, width, sub, qy, qc, 0, coefs);
+}
+
+/* dct_fixed != 0: the [ext] fixed-point DCT mode (dct_block_fixed) instead of the model's float64 DCT */
+int b2jo_encode_coefficients_ex(const uint8_t *rgb, int height, int width, int sub,
+                                const uint8_t *qy, const uint8_t *qc, int dct_fixed, int16_t *coefs)
 {
     geo_t g;
     if (make_geo(height, width, sub, &g)) return -1;
@@ -202,7 +265,7 @@ int b2jo_encode_coefficients(const uint8_t *rgb, int height, int width, int sub,
                     }
                     q = qc;
                 }
-                dct_block(blk, d);
+                if (dct_fixed) dct_block_fixed(blk, d); else dct_block(blk, d);
                 for (int i = 0; i < 64; i++) out[b * 64 + ZIGZAG[i]] = (int16_t)quant1(d[i], q[i]);
             }
         }
@@ -410,10 +473,13 @@ int b2jo_jfif_header(int height, int width, int sub, const uint8_t *qy, const ui
     return (int)(p - out);
 }
 
-/* RGB -> JFIF file.  Returns bytes needed (> cap: truncated), < 0 on error. */
+/* RGB -> JFIF file.  Returns bytes needed (> cap: truncated), < 0 on error.
+ * zrl: 0 eager / 1 standard, optionally | 0x100 for the [ext] fixed-point DCT mode. */
 int64_t b2jo_encode_jpeg(const uint8_t *rgb, int height, int width, int sub, int quality, int zrl,
                          uint8_t *out, int64_t cap)
 {
+    const int dct_fixed = (zrl & 0x100) != 0;
+    zrl &= 0xFF;
     geo_t g;
     if (make_geo(height, width, sub, &g)) return -1;
     if (cap < 1024) return -2;
@@ -421,7 +487,7 @@ int64_t b2jo_encode_jpeg(const uint8_t *rgb, int height, int width, int sub, int
     b2jo_quant_tables(quality, qy, qc);
     int16_t *coefs = (int16_t *)malloc((size_t)g.n_mcu * g.bpm * 64 * sizeof(int16_t));
     if (!coefs) return -3;
-    b2jo_encode_coefficients(rgb, height, width, sub, qy, qc, coefs);
+    b2jo_encode_coefficients_ex(rgb, height, width, sub, qy, qc, dct_fixed, coefs);
     int hl = b2jo_jfif_header(height, width, sub, qy, qc, out);
     int64_t n = b2jo_entropy_encode(coefs, height, width, sub, zrl, out + hl, cap - hl - 2 > 0 ? cap - hl - 2 : 0, NULL);
     free(coefs);

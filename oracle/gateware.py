@@ -138,6 +138,52 @@ def ycbcr444to422(y, cb, cr):
     return y, cb_cr
 
 
+def dct_1d_fixed(v):
+    """One pass of `DCTDatapath.dct1D`, litejpeg/core/new_dct6.py:171-396, on int64 arrays v[0..7]
+    (any trailing shape), with the datapath's own constants and shift points (:219-230: 1004/1024,
+    213/256, 49/128, 25/128, 569/1024, 473/512; :345, :370 sqrt2 = 181/128; every product is
+    floor(c*x / 2^s), `>>` on a sign-extended signal) but
+      * the two wiring slips of the source corrected so that the graph is the model's
+        (enc_frame.py:54-84): :262-263 feeds vector8[4] instead of vector8[7] into the sine product
+        of the (4,7) rotation, and :294 subtracts vector84Finalcos where v4*sin belongs;
+      * sums kept in wide integers (the 12-bit signals of the source wrap when |mean-128| > 32).
+    This is the [ext] "fixed" DCT mode of SURVEY 8f-3: NOT parity with the float64 model."""
+    v = [np.asarray(x).astype(np.int64) for x in v]
+
+    def bf(i, j):
+        v[i], v[j] = v[i] + v[j], v[i] - v[j]
+    bf(3, 4); bf(2, 5); bf(1, 6); bf(0, 7)                                  # stage 1  :192-195
+    bf(0, 3); bf(1, 2)                                                      # stage 2  :201-202
+    v4, v7, v5, v6 = v[4], v[7], v[5], v[6]
+    v[4] = ((213 * v4) >> 8) + ((569 * v7) >> 10)                           # :245-263, :291 (corrected)
+    v[7] = ((213 * v7) >> 8) - ((569 * v4) >> 10)                           # :294 (corrected)
+    v[5] = ((1004 * v5) >> 10) + ((25 * v6) >> 7)                           # :265-293
+    v[6] = ((1004 * v6) >> 10) - ((25 * v5) >> 7)
+    bf(7, 5); bf(4, 6); bf(0, 1)                                            # stage 3  :300-302
+    fa = ((49 * v[2]) >> 7) + ((473 * v[3]) >> 9)                           # :304-336
+    fs = ((49 * v[3]) >> 7) - ((473 * v[2]) >> 9)
+    v[2], v[3] = (181 * fa) >> 7, (181 * fs) >> 7                           # :338-360
+    r = [None] * 8                                                          # stage 4  :364-396
+    r[1], r[7] = v[7] + v[4], v[7] - v[4]
+    r[5], r[3] = (181 * v[6]) >> 7, (181 * v[5]) >> 7
+    r[6], r[2], r[4], r[0] = v[3], v[2], v[1], v[0]
+    return r
+
+
+def dct_fixed(blocks):
+    """`DCTDatapath`, new_dct6.py:107-145, with dct_1d_fixed: level shift -128 (:111), dct1D on the
+    rows (:114-115), on the columns (:118-127), arithmetic >> 3 (:136-140).  blocks (..., 64)
+    samples 0..255 row-major -> (..., 64) int64."""
+    b = np.asarray(blocks).astype(np.int64)
+    shp = b.shape
+    m = b.reshape(-1, 8, 8) - 128
+    rows = dct_1d_fixed([m[:, :, k] for k in range(8)])                    # along each row
+    m = np.stack(rows, axis=2)
+    cols = dct_1d_fixed([m[:, k, :] for k in range(8)])                    # along each column
+    m = np.stack(cols, axis=1)
+    return (m >> 3).reshape(shp)
+
+
 # litejpeg/core/quantization.py:20-27 (Annex-K luminance, unscaled)
 quant_values = np.array([
     16, 11, 10, 16, 24, 40, 51, 61,

@@ -54,14 +54,21 @@ class OracleC:
         self.lib.b2jo_quant_tables(int(quality), self._p(qy), self._p(qc))
         return qy, qc
 
-    def coefficients(self, rgb, sub, qy, qc):
+    def dct_fixed(self, blocks):
+        inp = np.ascontiguousarray(blocks, dtype=np.int32).reshape(-1, 64)
+        out = np.zeros_like(inp)
+        assert self.lib.b2jo_dct_fixed(self._p(inp), ctypes.c_int64(inp.shape[0]), self._p(out)) == 0
+        return out
+
+    def coefficients(self, rgb, sub, qy, qc, dct_fixed=False):
         rgb = np.ascontiguousarray(rgb)
         h, w = rgb.shape[:2]
         g = self.geometry(h, w, sub)
         qy = np.ascontiguousarray(qy, dtype=np.uint8)
         qc = np.ascontiguousarray(qc, dtype=np.uint8)
         coefs = np.zeros((g["n_mcu"], g["blocks_per_mcu"], 64), np.int16)
-        rc = self.lib.b2jo_encode_coefficients(self._p(rgb), h, w, int(sub), self._p(qy), self._p(qc), self._p(coefs))
+        rc = self.lib.b2jo_encode_coefficients_ex(self._p(rgb), h, w, int(sub), self._p(qy), self._p(qc), int(bool(dct_fixed)),
+                                                  self._p(coefs))
         assert rc == 0
         return coefs
 

@@ -255,3 +255,32 @@ def test_strided_input_through_the_c_abi(lj, oracle_c):
                                                coefs.data_ptr(), variant, torch.cuda.current_stream().cuda_stream))
         exp = oracle_c.coefficients(big[y0:y0 + crop_h, x0:x0 + crop_w].cpu().numpy(), "420", *J.quant_tables(75))
         assert np.array_equal(coefs.cpu().numpy()[0], exp.reshape(-1, 64)), variant
+
+
+@pytest.mark.parametrize("sub", SUBS)
+def test_fixed_dct_mode_equals_its_oracle(lj, oracle_c, sub):
+    """[ext] dct="fixed" (gateware fixed-point arithmetic): bit-exact against its own
+    restatement through both K1 variants and the whole encode; a valid file; near the model's."""
+    from PIL import Image
+    s = synth(lj)
+    frames = torch.stack([s.frame(136, 1048, 11, i) for i in range(2)])
+    enc = lj.JpegEncoder(sub, quality=75, dct="fixed", out_cap=136 * 1048 * 6)
+    qy, qc = oracle_c.quant_tables(75)
+    for variant in ("tiled", "simple"):
+        got = enc.coefficients(frames.cuda(), variant=variant).cpu().numpy()
+        for i in range(2):
+            want = oracle_c.coefficients(frames[i].numpy(), sub, qy, qc, dct_fixed=True).reshape(-1, 64)
+            assert np.array_equal(got[i], want), (variant, i)
+    files = enc.encode(frames.cuda())
+    model_files = lj.JpegEncoder(sub, quality=75, out_cap=136 * 1048 * 6).encode(frames.cuda())
+    for i in range(2):
+        assert files[i] == oracle_c.encode_jpeg(frames[i].numpy(), sub, 75, 0 | 0x100)
+        a = np.asarray(Image.open(io.BytesIO(files[i])).convert("RGB")).astype(np.float64)
+        b = np.asarray(Image.open(io.BytesIO(model_files[i])).convert("RGB")).astype(np.float64)
+        assert a.shape == (136, 1048, 3)
+        psnr = 10 * np.log10(255 ** 2 / np.mean((a - b) ** 2))
+        assert psnr > 35, psnr                         # the two arithmetic modes decode to nearly the same picture
+    host = lj.JpegEncoder(sub, quality=75, dct="fixed", out_cap=136 * 1048 * 6)
+    out_h, sizes_h = host.encode_host(frames)
+    assert bytes(out_h[1, :int(sizes_h[1])].numpy().tobytes()) == files[1]
+    host.close()

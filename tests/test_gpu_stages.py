@@ -210,3 +210,18 @@ def test_empty_and_ragged_inputs(lj):
     with pytest.raises(ValueError):
         lj.RunLength().process(lj.Packet([]))
     assert lj.RGB2YCbCr().process(lj.Packet([])) == []
+
+
+def test_dct_fixed_mode_operator(lj, oracle_c, golden):
+    """[ext] DCT(mode="fixed"): the gateware datapath's arithmetic (new_dct6.py:171-396, corrected)."""
+    from oracle import gateware as G
+    rng = np.random.default_rng(3)
+    blocks = np.concatenate([rng.integers(0, 256, (500, 64)), golden.stages["dct_in"][:100],
+                             np.full((1, 64), 0), np.full((1, 64), 255)])
+    op = lj.DCT(mode="fixed")
+    got = op.process(torch.tensor(blocks, dtype=torch.int16).cuda()).cpu().numpy()
+    assert np.array_equal(got, G.dct_fixed(blocks))
+    pk = op.process(lj.Packet(blocks[0].tolist()))
+    assert lj.to_signed(pk, 12) == G.dct_fixed(blocks[0]).tolist()
+    with pytest.raises(ValueError):
+        lj.DCT(mode="gateware")

@@ -77,3 +77,20 @@ def test_c_special_content(oracle_c):
         for sub in ("444", "422", "420"):
             for q in (50, 100):
                 assert oracle_c.encode_jpeg(rgb, sub, q, 0) == J.encode_jpeg(rgb, sub, q, "eager")
+
+
+def test_fixed_dct_mode_c_equals_numpy_and_stays_near_the_model(oracle_c, golden):
+    """[ext] dct_mode="fixed" (SURVEY 8f-3): the gateware datapath's constants and shift points
+    (new_dct6.py:171-396), wiring slips corrected.  The two restatements agree bit for bit; the
+    mode is NOT parity with the float64 model: measured deviation <= 4 LSB per coefficient."""
+    from oracle import gateware as G
+    from oracle import model_np as M
+    rng = np.random.default_rng(7)
+    blocks = np.concatenate([rng.integers(0, 256, (3000, 64)), golden.stages["dct_in"],
+                             np.full((1, 64), 0), np.full((1, 64), 255), np.full((1, 64), 128)])
+    f = G.dct_fixed(blocks)
+    assert np.array_equal(oracle_c.dct_fixed(blocks), f)
+    dev = np.abs(f - M.dct(blocks))
+    assert dev.max() <= 4 and dev.mean() < 1.0
+    assert f[-3, 0] == -1024 and f[-2, 0] == 1016 and not f[-1].any()      # flat blocks: exact DC, no AC
+    assert not f[-3, 1:].any() and not f[-2, 1:].any()
