@@ -67,6 +67,7 @@ def parse():
     ap.add_argument("--config", default="2", choices=sorted(PRESETS), help="BASELINE.json config (default 2, the headline)")
     ap.add_argument("--dct", default="model", choices=["model", "fixed"],
                     help="model = float64 model arithmetic (parity path, the headline); fixed = [ext] gateware fixed point, non-parity")
+    ap.add_argument("--restart", type=int, default=0, help="[ext] restart interval in MCUs (0 = none, the headline)")
     ap.add_argument("--kind", default="photo", choices=["photo", "noise", "grey"], help="synthetic content (SURVEY 8d stress)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
@@ -81,6 +82,8 @@ def parse():
         WORKLOAD += " [content: %s]" % KIND
     if args.dct != "model":
         WORKLOAD += " [dct: %s, NON-PARITY arithmetic mode]" % args.dct
+    if args.restart:
+        WORKLOAD += " [restart interval: %d MCUs]" % args.restart
     return args
 
 
@@ -265,10 +268,12 @@ def main():
     qy_a, qc_a = lj._lib.table_arg(qy), lj._lib.table_arg(qc)
     zrl = lj._lib.ZRL[ZRL]
     dct_flag = lj._lib.DCT_MODE[args.dct]
+    ent_opts = zrl | lj._lib.opt_restart(args.restart)
     cap = int(L.b2j_default_out_cap(ctypes.byref(desc)))
     nblk = frames * geo.blocks_per_frame
     coefs = torch.empty((nblk, 64), dtype=torch.int16, device=dev)
-    ent_ws = torch.empty((L.b2j_entropy_workspace_bytes(ctypes.byref(desc), cap) + 256,), dtype=torch.uint8, device=dev)
+    ent_ws = torch.empty((L.b2j_entropy_workspace_bytes_opts(ctypes.byref(desc), cap, lj._lib.opt_restart(args.restart)) + 256,),
+                         dtype=torch.uint8, device=dev)
     ent_ptr = (ent_ws.data_ptr() + 255) & ~255
     out = torch.empty((frames, cap), dtype=torch.uint8, device=dev)
     sizes = torch.empty((frames,), dtype=torch.int64, device=dev)
@@ -281,7 +286,7 @@ def main():
         if ev: ev[0].record(stream)
         lj._lib.check(L.b2j_fused_block(rgb.data_ptr(), dref, qy_a, qc_a, coefs.data_ptr(), dct_flag, sp))
         if ev: ev[1].record(stream)
-        lj._lib.check(L.b2j_entropy_encode(coefs.data_ptr(), dref, qy_a, qc_a, zrl, ent_ptr, out.data_ptr(), cap,
+        lj._lib.check(L.b2j_entropy_encode(coefs.data_ptr(), dref, qy_a, qc_a, ent_opts, ent_ptr, out.data_ptr(), cap,
                                            sizes.data_ptr(), sp))
         if ev: ev[2].record(stream)
 
@@ -295,7 +300,7 @@ def main():
     torch.cuda.synchronize()
     sz = sizes.cpu()
     assert int(sz.min()) > 0, "a frame did not fit its output slot"
-    enc = lj.JpegEncoder(SUB, quality=QUALITY, zrl=ZRL, dct=args.dct)
+    enc = lj.JpegEncoder(SUB, quality=QUALITY, zrl=ZRL, dct=args.dct, restart_interval=args.restart)
     out2, sz2 = enc.encode_device(rgb)
     torch.cuda.synchronize()
     assert torch.equal(sz2.cpu(), sz) and torch.equal(out2[0, :int(sz[0])], out[0, :int(sz[0])])
@@ -333,7 +338,7 @@ def main():
     if not args.skip_e2e:
         out_host = torch.empty((frames, cap), dtype=torch.uint8).pin_memory()
         sizes_host = torch.empty((frames,), dtype=torch.int64)
-        henc = lj.JpegEncoder(SUB, quality=QUALITY, zrl=ZRL, out_cap=cap, dct=args.dct)
+        henc = lj.JpegEncoder(SUB, quality=QUALITY, zrl=ZRL, out_cap=cap, dct=args.dct, restart_interval=args.restart)
         fpc = max(1, 16 * 1080 * 1920 // (H * W))
         for _ in range(2):
             henc.encode_host(host, out_host, sizes_host, frames_per_chunk=fpc)
@@ -397,7 +402,7 @@ def main():
                         "other instructions per 8x8 block-equivalent (DESIGN.md)"}
 
     base = None
-    if not args.skip_cpu_baseline and n_gpus == 1 and args.dct == "model":        # reported on rank 0 at N = 1 only
+    if not args.skip_cpu_baseline and n_gpus == 1 and args.dct == "model" and not args.restart:        # reported on rank 0 at N = 1 only
         base, _ = cpu_baseline(host, 1)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,

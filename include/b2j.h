@@ -65,8 +65,16 @@ extern "C" {
  * model.  NOT parity with the model (<= 4 LSB per coefficient before
  * quantisation); checked against its own restatement oracle/gateware.py. */
 #define B2J_FUSED_DCT_FIXED 0x100
-/* the same choice for b2j_encode / b2j_encoder_create, OR-ed into `zrl` */
+/* The `zrl` argument of b2j_entropy_encode, b2j_encode and b2j_encoder_create is an option word:
+ *   bits 0..7    B2J_ZRL_*
+ *   bit  8       B2J_OPT_DCT_FIXED (b2j_encode / b2j_encoder_create: K1 uses B2J_FUSED_DCT_FIXED)
+ *   bits 16..30  B2J_OPT_RESTART(n): [ext] restart interval of n MCUs, 1..32767 (T.81 B.2.4.4,
+ *                E.1.4; the reference has no counterpart): a DRI segment in the
+ *                header, and every n MCUs the byte is padded with 1s, RSTm (0xFFD0 + m mod 8)
+ *                is written and the DC predictors restart from 0.  Workspaces must then be
+ *                sized with the *_workspace_bytes_opts() queries. */
 #define B2J_OPT_DCT_FIXED 0x100
+#define B2J_OPT_RESTART(n) ((int)(n) << 16)
 
 /* A batch of equally sized, interleaved 8-bit RGB frames (H x W x 3, like the
  * array the model reads at test/model/enc_frame.py:7-10). */
@@ -208,6 +216,7 @@ int b2j_bitpack(const int16_t *coefs, const uint32_t *offsets, const int64_t *to
  * header and EOI follow.  Same outputs as b2j_block_bits + b2j_scan + b2j_bitpack.
  * workspace: b2j_entropy_workspace_bytes() bytes, 256-byte aligned. */
 size_t b2j_entropy_workspace_bytes(const b2j_image_desc *desc, int64_t out_cap);
+size_t b2j_entropy_workspace_bytes_opts(const b2j_image_desc *desc, int64_t out_cap, int opts);
 int b2j_entropy_encode(const int16_t *coefs, const b2j_image_desc *desc,
                        const uint8_t qy_host[64], const uint8_t qc_host[64], int zrl,
                        void *workspace, uint8_t *out, int64_t out_cap, int64_t *sizes, void *stream);
@@ -216,6 +225,7 @@ int b2j_entropy_encode(const int16_t *coefs, const b2j_image_desc *desc,
  * quality 1..100 picks the [ext] IJG tables, or pass quality = 0 and explicit
  * tables.  zrl: B2J_ZRL_*, optionally | B2J_OPT_DCT_FIXED. */
 size_t b2j_encode_workspace_bytes(const b2j_image_desc *desc, int64_t out_cap);
+size_t b2j_encode_workspace_bytes_opts(const b2j_image_desc *desc, int64_t out_cap, int opts);
 int64_t b2j_default_out_cap(const b2j_image_desc *desc);
 int b2j_encode(const uint8_t *rgb, const b2j_image_desc *desc, int quality,
                const uint8_t qy_host[64], const uint8_t qc_host[64], int zrl,

@@ -63,8 +63,10 @@ SIGNATURES = {
     "b2j_bitpack_workspace_bytes": (c_size_t, [_DESC, c_int64]),
     "b2j_bitpack": (c_int, [_P, _P, _P, _DESC, _P, _P, c_int, _P, _P, c_int64, _P, _P]),
     "b2j_entropy_workspace_bytes": (c_size_t, [_DESC, c_int64]),
+    "b2j_entropy_workspace_bytes_opts": (c_size_t, [_DESC, c_int64, c_int]),
     "b2j_entropy_encode": (c_int, [_P, _DESC, _P, _P, c_int, _P, _P, c_int64, _P, _P]),
     "b2j_encode_workspace_bytes": (c_size_t, [_DESC, c_int64]),
+    "b2j_encode_workspace_bytes_opts": (c_size_t, [_DESC, c_int64, c_int]),
     "b2j_default_out_cap": (c_int64, [_DESC]),
     "b2j_encode": (c_int, [_P, _DESC, c_int, _P, _P, c_int, _P, c_size_t, _P, c_int64, _P, _P]),
     "b2j_encode_launch_count": (c_int, [_DESC]),
@@ -79,6 +81,14 @@ ZRL = {"eager": 0, "standard": 1}
 CSC = {"jfif": 0, "xapp930": 1}
 QMODE = {"round": 0, "trunc": 1, "reciprocal": 2}
 DCT_MODE = {"model": 0, "fixed": 0x100}      # B2J_FUSED_DCT_FIXED / B2J_OPT_DCT_FIXED
+
+
+def opt_restart(n):
+    """B2J_OPT_RESTART(n): restart interval in MCUs for the option word (0 = none)."""
+    n = int(n)
+    if not 0 <= n <= 32767:
+        raise ValueError("restart_interval must be in 0..32767 MCUs")
+    return n << 16
 FUSED = {"auto": 0, "simple": 1, "tiled": 2}
 
 _lib = None

@@ -138,7 +138,7 @@ static uint8_t *seg(uint8_t *p, int marker, const uint8_t *payload, int n)
 
 // [ext] SOI, APP0 (JFIF 1.01), DQT x2 (zig-zag order), SOF0, DHT x4, SOS.  The
 // reference only sketches this (test/model/enc_frame.py:189-200).
-int jfif_header(const Geo &g, const uint8_t *qy, const uint8_t *qc, uint8_t *out)
+int jfif_header(const Geo &g, const uint8_t *qy, const uint8_t *qc, uint8_t *out, int restart_interval)
 {
     uint8_t *p = out, buf[256];
     *p++ = 0xFF; *p++ = 0xD8;
@@ -163,6 +163,10 @@ int jfif_header(const Geo &g, const uint8_t *qy, const uint8_t *qc, uint8_t *out
             buf[0] = id[t]; memcpy(buf + 1, bits[t], 16); memcpy(buf + 17, vals[t], (size_t)nv[t]);
             p = seg(p, 0xC4, buf, 17 + nv[t]);
         }
+    }
+    if (restart_interval > 0) {        // [ext] DRI, T.81 B.2.4.4
+        const uint8_t dri[2] = {(uint8_t)(restart_interval >> 8), (uint8_t)restart_interval};
+        p = seg(p, 0xDD, dri, 2);
     }
     { const uint8_t sos[10] = {3, 1, 0x00, 2, 0x11, 3, 0x11, 0, 63, 0}; p = seg(p, 0xDA, sos, 10); }
     return (int)(p - out);

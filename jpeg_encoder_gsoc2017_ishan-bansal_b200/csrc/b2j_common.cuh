@@ -45,6 +45,7 @@ struct Geo {
 int make_geo(const b2j_image_desc *d, Geo *g);
 
 static const int kHeaderBytes = 623;   // SOI APP0 DQTx2 SOF0 DHTx4 SOS
+static const int kHeaderMax = 640;     // + DRI (6 bytes) when a restart interval is set
 
 // Quantisation multipliers for the fused kernel: q = (|c| * mul + 2^19) >> 20
 // reproduces round-half-away(|c| / d) for every |c| <= 1024, d in 1..255
@@ -77,7 +78,7 @@ struct HuffLut {
 };
 const HuffLut &host_huff_lut();
 
-int jfif_header(const Geo &g, const uint8_t *qy, const uint8_t *qc, uint8_t *out /* >= kHeaderBytes */);
+int jfif_header(const Geo &g, const uint8_t *qy, const uint8_t *qc, uint8_t *out /* >= kHeaderMax */, int restart_interval = 0);
 
 static inline void *as_ptr(void *p) { return p; }
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }

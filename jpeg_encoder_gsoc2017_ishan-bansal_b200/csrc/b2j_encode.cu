@@ -14,17 +14,17 @@ struct WsLayout {
     size_t coefs, entropy_ws, total;
 };
 
-int ws_layout(const b2j_image_desc *desc, int64_t out_cap, WsLayout *w)
+int ws_layout(const b2j_image_desc *desc, int64_t out_cap, int opts, WsLayout *w)
 {
     Geo g;
     int rc = make_geo(desc, &g);
     if (rc) return rc;
-    B2J_REQUIRE(out_cap >= kHeaderBytes + 2, B2J_E_CAPACITY, "out_cap %lld smaller than the JFIF header", (long long)out_cap);
+    B2J_REQUIRE(out_cap >= kHeaderMax + 2, B2J_E_CAPACITY, "out_cap %lld smaller than the JFIF header", (long long)out_cap);
     B2J_REQUIRE(g.n_frames <= 65535, B2J_E_SHAPE, "at most 65535 frames per call");
     const size_t nb = (size_t)g.n_frames * (size_t)g.blocks_per_frame;
     size_t o = 0;
     w->coefs = o; o = align_up(o + nb * 64 * sizeof(int16_t), 256);
-    w->entropy_ws = o; o = align_up(o + b2j_entropy_workspace_bytes(desc, out_cap), 256);
+    w->entropy_ws = o; o = align_up(o + b2j_entropy_workspace_bytes_opts(desc, out_cap, opts & ~B2J_OPT_DCT_FIXED), 256);
     w->total = o;
     return B2J_OK;
 }
@@ -41,10 +41,17 @@ extern "C" int64_t b2j_default_out_cap(const b2j_image_desc *desc)
     return (px * 3 / 2 + 4096 + 15) & ~15LL;
 }
 
+extern "C" size_t b2j_encode_workspace_bytes_opts(const b2j_image_desc *desc, int64_t out_cap, int opts)
+{
+    WsLayout w;
+    if (ws_layout(desc, out_cap, opts, &w)) return 0;
+    return w.total;
+}
+
 extern "C" size_t b2j_encode_workspace_bytes(const b2j_image_desc *desc, int64_t out_cap)
 {
     WsLayout w;
-    if (ws_layout(desc, out_cap, &w)) return 0;
+    if (ws_layout(desc, out_cap, 0, &w)) return 0;
     return w.total;
 }
 
@@ -70,7 +77,7 @@ extern "C" int b2j_encode(const uint8_t *rgb, const b2j_image_desc *desc, int qu
         memcpy(qc, qc_host, 64);
     }
     WsLayout w;
-    int rc = ws_layout(desc, out_cap, &w);
+    int rc = ws_layout(desc, out_cap, zrl, &w);
     if (rc) return rc;
     B2J_REQUIRE(workspace_bytes >= w.total, B2J_E_WORKSPACE, "b2j_encode: workspace %zu < %zu bytes", workspace_bytes, w.total);
     uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
@@ -119,7 +126,7 @@ extern "C" int b2j_encoder_create(b2j_encoder **enc, const b2j_image_desc *desc,
 {
     B2J_REQUIRE(enc && desc, B2J_E_ARG, "b2j_encoder_create: null pointer");
     B2J_REQUIRE(quality >= 1 && quality <= 100, B2J_E_ARG, "b2j_encoder_create: quality %d not in 1..100", quality);
-    B2J_REQUIRE((zrl & ~B2J_OPT_DCT_FIXED) == B2J_ZRL_EAGER || (zrl & ~B2J_OPT_DCT_FIXED) == B2J_ZRL_STANDARD, B2J_E_ARG,
+    B2J_REQUIRE((zrl & 0xFF) == B2J_ZRL_EAGER || (zrl & 0xFF) == B2J_ZRL_STANDARD, B2J_E_ARG,
                 "b2j_encoder_create: bad zrl policy");
     B2J_REQUIRE(frames_per_chunk >= 1, B2J_E_ARG, "b2j_encoder_create: frames_per_chunk must be >= 1");
     B2J_REQUIRE(desc->row_stride == 0 && desc->frame_stride == 0, B2J_E_ARG, "b2j_encoder_create: host frames must be packed");
@@ -134,7 +141,7 @@ extern "C" int b2j_encoder_create(b2j_encoder **enc, const b2j_image_desc *desc,
     memset(e, 0, sizeof *e);
     e->desc = d; e->quality = quality; e->zrl = zrl; e->out_cap = out_cap;
     e->frame_bytes = (size_t)g.height * (size_t)g.width * 3;
-    e->ws_bytes = b2j_encode_workspace_bytes(&d, out_cap);
+    e->ws_bytes = b2j_encode_workspace_bytes_opts(&d, out_cap, zrl);
     if (!e->ws_bytes) { encoder_free(e); return B2J_E_CAPACITY; }
     for (int s = 0; s < b2j_encoder::kSlots; s++) {
         cudaError_t err;

@@ -211,58 +211,108 @@ __global__ void __launch_bounds__(256) k_ff_count(const uint8_t *__restrict__ un
     if (threadIdx.x == 0) ffpart[(long long)f * chunks + ch] = tot;
 }
 
-// one CTA per frame: exclusive scan of 0xFF counts; final size / capacity verdict
+// One CTA per frame.  A frame is nseg independently packed streams ("segments": 1 without restart
+// intervals); ffpart, total_bits and segbase are indexed by frame * nseg + segment.
+//   1. per segment (one warp each): exclusive scan of the 0xFF counts of its 4096-byte chunks, in
+//      place; segment size = bytes + 0xFF count + 2 (the RSTm / EOI marker that follows it);
+//   2. exclusive scan of the segment sizes -> segbase; final file size / capacity verdict.
 __global__ void __launch_bounds__(256) k_ff_scan(uint32_t *__restrict__ ffpart, const int64_t *__restrict__ total_bits,
-                                                 int64_t *__restrict__ sizes, long long ucap, long long out_cap, int chunks,
-                                                 int header_bytes, const int *__restrict__ error_flag)
+                                                 uint32_t *__restrict__ segbase, int64_t *__restrict__ sizes, long long ucap,
+                                                 long long out_cap, int chunks, int nseg, int header_bytes,
+                                                 const int *__restrict__ error_flag)
 {
     __shared__ uint32_t s_warp[8];
-    uint32_t *p = ffpart + (long long)blockIdx.x * chunks;
+    __shared__ int s_over;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long f = blockIdx.x;
+    uint32_t *fp = ffpart + f * nseg * chunks;
+    const int64_t *tb = total_bits + f * nseg;
+    uint32_t *sb = segbase + f * nseg;
+    if (threadIdx.x == 0) s_over = 0;
+    __syncthreads();
+    if (nseg == 1) {                                                // one long segment: the whole CTA scans its chunks
+        unsigned long long c0 = 0;
+        for (int base = 0; base < chunks; base += 256) {
+            const int i = base + threadIdx.x;
+            const uint32_t v = i < chunks ? fp[i] : 0u;
+            uint32_t tot;
+            const uint32_t ex = cta_excl_scan_256(v, s_warp, &tot);
+            if (i < chunks) fp[i] = (uint32_t)c0 + ex;
+            c0 += tot;
+        }
+        if (threadIdx.x == 0) {
+            const long long nb = (tb[0] + 7) >> 3;
+            if (nb > ucap) s_over = 1;
+            sb[0] = (uint32_t)c0 + (uint32_t)nb + 2u;
+        }
+    } else {
+        for (int k = warp; k < nseg; k += 8) {                      // many short segments: one warp each
+            uint32_t *p = fp + (long long)k * chunks;
+            uint32_t carry = 0;
+            for (int base = 0; base < chunks; base += 32) {
+                const int i = base + lane;
+                const uint32_t v = i < chunks ? p[i] : 0u;
+                const uint32_t inc = warp_incl_scan(v);
+                if (i < chunks) p[i] = carry + inc - v;
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0) {
+                const long long nb = (tb[k] + 7) >> 3;
+                if (nb > ucap) s_over = 1;
+                sb[k] = carry + (uint32_t)nb + 2u;
+            }
+        }
+    }
+    __syncthreads();
     unsigned long long carry = 0;
-    for (int base = 0; base < chunks; base += 256) {
+    for (int base = 0; base < nseg; base += 256) {
         const int i = base + threadIdx.x;
-        const uint32_t v = i < chunks ? p[i] : 0u;
+        const uint32_t v = i < nseg ? sb[i] : 0u;
         uint32_t tot;
         const uint32_t ex = cta_excl_scan_256(v, s_warp, &tot);
-        if (i < chunks) p[i] = (uint32_t)carry + ex;
+        if (i < nseg) sb[i] = (uint32_t)carry + ex;
         carry += tot;
     }
     if (threadIdx.x == 0) {
-        const long long nbytes = (total_bits[blockIdx.x] + 7) >> 3;
-        if (error_flag && *error_flag) sizes[blockIdx.x] = (int64_t)0x8000000000000000LL;     // internal error
-        else if (nbytes > ucap) sizes[blockIdx.x] = -(header_bytes + 2 * nbytes + 2);      // upper bound of the need
+        if (error_flag && *error_flag) sizes[f] = (int64_t)0x8000000000000000LL;            // internal error
+        else if (s_over) sizes[f] = -(header_bytes + 2 * (long long)carry);                 // upper bound of the need
         else {
-            const long long need = header_bytes + nbytes + (long long)carry + 2;
-            sizes[blockIdx.x] = need <= out_cap ? need : -need;
+            const long long need = header_bytes + (long long)carry;
+            sizes[f] = need <= out_cap ? need : -need;
         }
     }
 }
 
 
-// grid (x, frames): the CTAs of a frame stride over the chunks the stream really has (the grid is
-// sized from the slot capacity, which is several times the typical stream: empty CTAs cost more
-// than the copy itself).
+// grid (segments of all frames, y): the CTAs of a segment stride over the chunks its stream really
+// has (the slot capacity is several times the typical stream: empty CTAs cost more than the copy).
+// The first segment's first CTA writes the header; the CTA that writes a segment's last chunk
+// appends the marker that follows it: RSTm between segments, EOI after the last one.
 __global__ void __launch_bounds__(256) k_stuff_write(const uint8_t *__restrict__ unstuffed, const int64_t *__restrict__ total_bits,
-                                                     const uint32_t *__restrict__ ffpart, const int64_t *__restrict__ sizes,
-                                                     uint8_t *__restrict__ out, long long ucap, long long out_cap, int chunks,
+                                                     const uint32_t *__restrict__ ffpart, const uint32_t *__restrict__ segbase,
+                                                     const int64_t *__restrict__ sizes, uint8_t *__restrict__ out, long long ucap,
+                                                     long long out_cap, int chunks, int nseg,
                                                      const __grid_constant__ HeaderParam H)
 {
     __shared__ uint32_t s_warp[8];
     __shared__ __align__(16) uint8_t s_out[2 * kStuffChunk + 16];
-    const int f = blockIdx.y;
+    const long long vf = blockIdx.x;
+    const long long f = vf / nseg;
+    const int seg = (int)(vf % nseg);
     if (sizes[f] < 0) return;                                       // slot too small: leave it untouched
-    const long long nbytes = (total_bits[f] + 7) >> 3;
-    uint8_t *dst_frame = out + (long long)f * out_cap;
-    if (blockIdx.x == 0)
-        for (int i = threadIdx.x; i < kHeaderBytes; i += 256) dst_frame[i] = H.bytes[i];
-    for (int ch = blockIdx.x; (long long)ch * kStuffChunk < nbytes; ch += gridDim.x) {
+    const long long nbytes = (total_bits[vf] + 7) >> 3;
+    uint8_t *dst_frame = out + f * out_cap;
+    if (seg == 0 && blockIdx.y == 0)
+        for (int i = threadIdx.x; i < H.len; i += 256) dst_frame[i] = H.bytes[i];
+    uint8_t *dst_seg = dst_frame + H.len + segbase[vf];
+    for (int ch = blockIdx.y; (long long)ch * kStuffChunk < nbytes; ch += gridDim.y) {
         const long long pos = (long long)ch * kStuffChunk + threadIdx.x * 16;
         uint32_t m = 0;
         int nvalid = 0;
         uint4 q = make_uint4(0, 0, 0, 0);
         if (pos < nbytes) {
             nvalid = (int)min(16LL, nbytes - pos);
-            q = *reinterpret_cast<const uint4 *>(unstuffed + (long long)f * ucap + pos);
+            q = *reinterpret_cast<const uint4 *>(unstuffed + vf * ucap + pos);
             m = ff_mask16(q, nvalid);
         }
         uint32_t tot;
@@ -287,7 +337,7 @@ __global__ void __launch_bounds__(256) k_stuff_write(const uint8_t *__restrict__
         __syncthreads();
         const long long chunk_in = min((long long)kStuffChunk, nbytes - (long long)ch * kStuffChunk);
         const int n_out = (int)chunk_in + (int)tot;
-        uint8_t *dst = dst_frame + kHeaderBytes + (long long)ch * kStuffChunk + ffpart[(long long)f * chunks + ch];
+        uint8_t *dst = dst_seg + (long long)ch * kStuffChunk + ffpart[vf * chunks + ch];
         // head bytes up to 4-byte alignment, aligned words, tail bytes
         const int head = min(n_out, (int)((4 - ((uintptr_t)dst & 3)) & 3));
         if (threadIdx.x < head) dst[threadIdx.x] = s_out[threadIdx.x];
@@ -299,10 +349,10 @@ __global__ void __launch_bounds__(256) k_stuff_write(const uint8_t *__restrict__
         }
         const int done = head + 4 * nwords;
         if (threadIdx.x < n_out - done) dst[done + threadIdx.x] = s_out[done + threadIdx.x];
-        // EOI after the last chunk
+        // the marker after the segment's last chunk: RSTm (T.81 B.2.4.4 / E.1.4), or EOI after the last segment
         if ((long long)(ch + 1) * kStuffChunk >= nbytes && threadIdx.x == 0) {
             dst[n_out] = 0xFF;
-            dst[n_out + 1] = 0xD9;
+            dst[n_out + 1] = seg == nseg - 1 ? 0xD9 : (uint8_t)(0xD0 + (seg & 7));
         }
         __syncthreads();                                            // s_out and s_warp are reused by the next chunk
     }
@@ -312,22 +362,25 @@ static int scan_chunks(long long nblk) { return (int)((nblk + kScanChunk - 1) / 
 
 int launch_stuffing(const uint8_t *unstuffed, const int64_t *total_bits, uint32_t *ffpart, int64_t *sizes, uint8_t *out,
                     long long ucap, long long out_cap, int n_frames, const HeaderParam &H, const int *error_flag,
-                    bool counted, cudaStream_t st)
+                    bool counted, cudaStream_t st, int nseg)
 {
     const int schunks = stuff_chunks(ucap);
-    dim3 sgrid((unsigned)schunks, (unsigned)n_frames);
+    const long long nvf = (long long)n_frames * nseg;
+    uint32_t *segbase = ffpart + nvf * schunks;                     // [n_frames * nseg], after the chunk counts
     if (!counted) {
+        dim3 sgrid((unsigned)schunks, (unsigned)n_frames);
         k_ff_count<<<sgrid, 256, 0, st>>>(unstuffed, total_bits, ffpart, ucap, schunks);
         B2J_LAUNCH_CHECK("k_ff_count");
     }
-    k_ff_scan<<<(unsigned)n_frames, 256, 0, st>>>(ffpart, total_bits, sizes, ucap, out_cap, schunks, kHeaderBytes, error_flag);
+    k_ff_scan<<<(unsigned)n_frames, 256, 0, st>>>(ffpart, total_bits, segbase, sizes, ucap, out_cap, schunks, nseg, H.len,
+                                                  error_flag);
     B2J_LAUNCH_CHECK("k_ff_scan");
-    // enough CTAs per frame to fill the GPU a few times over, never more than the slot has chunks
-    int per_frame = (148 * 16 + n_frames - 1) / n_frames;
-    if (per_frame > schunks) per_frame = schunks;
-    if (per_frame < 1) per_frame = 1;
-    k_stuff_write<<<dim3((unsigned)per_frame, (unsigned)n_frames), 256, 0, st>>>(unstuffed, total_bits, ffpart, sizes, out, ucap,
-                                                                                 out_cap, schunks, H);
+    // enough CTAs per segment to fill the GPU a few times over, never more than the slot has chunks
+    long long per_seg = (148 * 16 + nvf - 1) / nvf;
+    if (per_seg > schunks) per_seg = schunks;
+    if (per_seg < 1) per_seg = 1;
+    k_stuff_write<<<dim3((unsigned)nvf, (unsigned)per_seg), 256, 0, st>>>(unstuffed, total_bits, ffpart, segbase, sizes, out, ucap,
+                                                                          out_cap, schunks, nseg, H);
     B2J_LAUNCH_CHECK("k_stuff_write");
     return B2J_OK;
 }
@@ -387,7 +440,7 @@ extern "C" size_t b2j_bitpack_workspace_bytes(const b2j_image_desc *desc, int64_
     Geo g;
     if (make_geo(desc, &g) || out_cap < kHeaderBytes + 2) return 0;
     const long long ucap = ucap_of(out_cap);
-    return (size_t)g.n_frames * (size_t)ucap + (size_t)g.n_frames * stuff_chunks(ucap) * sizeof(uint32_t) + 512;
+    return (size_t)g.n_frames * (size_t)ucap + (size_t)g.n_frames * (stuff_chunks(ucap) + 1) * sizeof(uint32_t) + 512;
 }
 
 extern "C" int b2j_bitpack(const int16_t *coefs, const uint32_t *offsets, const int64_t *total_bits,
@@ -409,7 +462,8 @@ extern "C" int b2j_bitpack(const int16_t *coefs, const uint32_t *offsets, const 
     uint32_t *ffpart = reinterpret_cast<uint32_t *>(unstuffed + (size_t)g.n_frames * (size_t)ucap);
     HeaderParam H;
     memset(&H, 0, sizeof H);
-    if (jfif_header(g, qy_host, qc_host, H.bytes) != kHeaderBytes) {
+    H.len = jfif_header(g, qy_host, qc_host, H.bytes);
+    if (H.len != kHeaderBytes) {
         set_error("b2j_bitpack: internal header length mismatch");
         return B2J_E_ARG;
     }

@@ -119,7 +119,7 @@ __device__ __forceinline__ uint32_t cta_excl_scan_256(uint32_t v, uint32_t *s_wa
 
 
 static constexpr int kStuffChunk = 4096;         // unstuffed bytes per CTA of the stuffing kernels
-struct HeaderParam { uint8_t bytes[kHeaderBytes + 1]; };
+struct HeaderParam { uint8_t bytes[kHeaderMax]; int len; };
 
 static inline LutParam make_lut_param()
 {
@@ -135,8 +135,11 @@ static inline int stuff_chunks(long long ucap) { return (int)((ucap + kStuffChun
 // error_flag may be null; when *error_flag != 0 every sizes[f] is set to INT64_MIN.
 // counted: ffpart already holds the 0xFF count of every 4096-byte chunk (the fused entropy kernel
 // counts while it composes the words), so the counting pass is skipped.
+// nseg > 1 ([ext] restart intervals): every frame is nseg consecutive, independently packed
+// streams ("segments": ucap, total_bits and ffpart are per segment, n_frames * nseg of them); they
+// are joined with RSTm markers between them.
 int launch_stuffing(const uint8_t *unstuffed, const int64_t *total_bits, uint32_t *ffpart, int64_t *sizes, uint8_t *out,
                     long long ucap, long long out_cap, int n_frames, const HeaderParam &H, const int *error_flag,
-                    bool counted, cudaStream_t st);
+                    bool counted, cudaStream_t st, int nseg = 1);
 
 }  // namespace b2j

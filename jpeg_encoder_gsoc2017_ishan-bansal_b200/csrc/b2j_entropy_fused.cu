@@ -46,8 +46,10 @@ struct FusedEntropyParams {
     uint32_t *ffpart;             // [n_frames][schunks]: 0xFF bytes per 4096-byte chunk of the packed stream (zeroed)
     int schunks;
     long long ucap;
-    int chunks;
-    EGeo e;
+    int chunks;                   // chunks per segment
+    int nseg;                     // [ext] restart intervals: segments per frame (1 = none); a segment is an independent,
+    long long frame_blocks;       // byte-aligned stream with its own DC predictors.  e.nblk = blocks per full segment,
+    EGeo e;                       // e.n_frames = frames * nseg; frame_blocks = blocks of a whole frame
 };
 
 __device__ __forceinline__ unsigned long long ld_volatile(const unsigned long long *p)
@@ -145,7 +147,7 @@ __device__ __forceinline__ void encode_block(uint32_t mlo, uint32_t mhi, int dif
     }
 }
 
-template <bool EAGER>
+template <bool EAGER, bool SEG>
 __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant__ FusedEntropyParams P,
                                                           const __grid_constant__ LutParam L)
 {
@@ -167,17 +169,28 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
     __syncthreads();
     const unsigned int id = s_misc[4];
     if (id >= total_chunks) break;
-    // tickets interleave the frames: consecutive CTAs work on different frames, so the predecessor
-    // chunk of the same frame was started n_frames tickets earlier and has usually published its
-    // inclusive prefix by the time it is needed (short look-back, no serial chain inside a wave)
+    // tickets interleave the streams: consecutive CTAs work on different streams, so the predecessor
+    // chunk of the same stream was started n_frames tickets earlier and has usually published its
+    // inclusive prefix by the time it is needed (short look-back, no serial chain inside a wave).
+    // A stream is a frame or, with [ext] restart intervals (SEG), one segment of a frame: segment
+    // f % nseg of frame f / nseg; the last segment of a frame may be short.
     const int f = (int)(id % (unsigned)P.e.n_frames), ch = (int)(id / (unsigned)P.e.n_frames);
     const EGeo &e = P.e;
+    long long nblk = e.nblk;
+    const int16_t *fc;
+    if (SEG) {
+        const long long seg0 = (long long)(f % P.nseg) * e.nblk;
+        nblk = min(e.nblk, P.frame_blocks - seg0);
+        fc = P.coefs + ((long long)(f / P.nseg) * P.frame_blocks + seg0) * 64;
+    } else {
+        fc = P.coefs + (long long)f * e.nblk * 64;
+    }
     const long long b0 = (long long)ch * kChunk;
-    const long long b1 = min(b0 + kChunk, e.nblk);
-    const long long bl = min(b1 + kLookahead, e.nblk);              // end of the lookahead blocks
+    if (SEG && b0 >= nblk) continue;                                 // chunk beyond a short last segment
+    const long long b1 = min(b0 + kChunk, nblk);
+    const long long bl = min(b1 + kLookahead, nblk);                // end of the lookahead blocks
     const int nown = (int)(b1 - b0), nall = (int)(bl - b0);
-    const int16_t *fc = P.coefs + (long long)f * e.nblk * 64;
-    const bool last = b1 >= e.nblk;
+    const bool last = b1 >= nblk;
 
     // ---- 1. coalesced load (16-byte pieces) into the padded layout + non-zero byte masks
     {
@@ -296,7 +309,7 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
     // tail of 4-6 bit blocks can sit entirely inside a word owned by the previous chunk, which
     // sees those blocks as its lookahead columns).
     const uint32_t total = (uint32_t)mybits;
-    const bool reaches_end = bl >= e.nblk;                           // columns 0..nall-1 run to the frame's end
+    const bool reaches_end = bl >= nblk;                             // columns 0..nall-1 run to the stream's end
     if (last && tid == nown - 1) P.total_bits[f] = (int64_t)((uint32_t)E + excl + total);
     if (tid < nown) {
         const uint32_t G = (uint32_t)E + excl;
@@ -344,53 +357,83 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
 
 using namespace b2j;
 
-static size_t fused_status_bytes(const Geo &g)
+// [ext] restart intervals: the option word's bits 16..30 give the interval in MCUs.  A frame then
+// is nseg independent streams ("segments") of `seg_blocks` blocks (the last one may be shorter).
+struct SegPlan {
+    int ri, nseg, chunks;         // interval (MCUs), segments per frame, 128-block chunks per segment
+    long long seg_blocks, ucap;   // blocks per full segment, unstuffed capacity per segment (bytes)
+};
+
+static SegPlan seg_plan(const Geo &g, int64_t out_cap, int opts)
 {
-    const size_t chunks = (size_t)((g.blocks_per_frame + kChunk - 1) / kChunk);
-    return 256 + (size_t)g.n_frames * chunks * sizeof(unsigned long long);
+    SegPlan sp;
+    const long long n_mcu = (long long)g.mcus_x * g.mcus_y;
+    sp.ri = (opts >> 16) & 0x7FFF;
+    sp.nseg = (sp.ri > 0 && sp.ri < n_mcu) ? (int)((n_mcu + sp.ri - 1) / sp.ri) : 1;
+    sp.seg_blocks = sp.nseg > 1 ? (long long)sp.ri * g.bpm : g.blocks_per_frame;
+    sp.ucap = ucap_of(out_cap);
+    if (sp.nseg > 1) {            // a block never needs more than 208 bytes (11+11 + 63 x (16+10) bits)
+        const long long worst = (sp.seg_blocks * 256 + 64 + 15) & ~15LL;
+        if (worst < sp.ucap) sp.ucap = worst;
+    }
+    sp.chunks = (int)((sp.seg_blocks + kChunk - 1) / kChunk);
+    return sp;
 }
 
 struct FusedWs { size_t status, ffpart, zero_bytes, total_bits, unstuffed, overflow, total; };
 
-static FusedWs fused_ws(const Geo &g, long long ucap)
+static FusedWs fused_ws(const Geo &g, const SegPlan &sp)
 {
     FusedWs w;
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t nvf = (size_t)g.n_frames * sp.nseg;
     w.status = 256;                                                     // [0,256): ticket, error flag
-    w.ffpart = up(w.status + fused_status_bytes(g) - 256);
-    w.zero_bytes = up(w.ffpart + (size_t)g.n_frames * stuff_chunks(ucap) * sizeof(uint32_t));   // [0, zero_bytes) is cleared per call
+    w.ffpart = up(w.status + nvf * sp.chunks * sizeof(unsigned long long));
+    // 0xFF counts per 4096-byte chunk, then one segment base each; [0, zero_bytes) is cleared per call
+    w.zero_bytes = up(w.ffpart + nvf * (stuff_chunks(sp.ucap) + 1) * sizeof(uint32_t));
     w.total_bits = w.zero_bytes;
-    w.unstuffed = up(w.total_bits + (size_t)g.n_frames * sizeof(int64_t));
-    w.overflow = up(w.unstuffed + (size_t)g.n_frames * (size_t)ucap);
+    w.unstuffed = up(w.total_bits + nvf * sizeof(int64_t));
+    w.overflow = up(w.unstuffed + nvf * (size_t)sp.ucap);
     w.total = w.overflow + (size_t)kMaxSlots * kOvfWords * kCols * sizeof(uint32_t);
     return w;
 }
 
-extern "C" size_t b2j_entropy_workspace_bytes(const b2j_image_desc *desc, int64_t out_cap)
+extern "C" size_t b2j_entropy_workspace_bytes_opts(const b2j_image_desc *desc, int64_t out_cap, int opts)
 {
     Geo g;
-    if (make_geo(desc, &g) || out_cap < kHeaderBytes + 2) return 0;
-    return fused_ws(g, ucap_of(out_cap)).total;
+    if (make_geo(desc, &g) || out_cap < kHeaderMax + 2) return 0;
+    return fused_ws(g, seg_plan(g, out_cap, opts)).total;
+}
+
+extern "C" size_t b2j_entropy_workspace_bytes(const b2j_image_desc *desc, int64_t out_cap)
+{
+    return b2j_entropy_workspace_bytes_opts(desc, out_cap, 0);
 }
 
 // K2..K4 in one pass over the coefficients: coefs -> JFIF files.
 extern "C" int b2j_entropy_encode(const int16_t *coefs, const b2j_image_desc *desc, const uint8_t qy_host[64],
-                                  const uint8_t qc_host[64], int zrl, void *workspace, uint8_t *out, int64_t out_cap,
+                                  const uint8_t qc_host[64], int opts, void *workspace, uint8_t *out, int64_t out_cap,
                                   int64_t *sizes, void *stream)
 {
+    const int zrl = opts & 0xFF;
     B2J_REQUIRE(coefs && qy_host && qc_host && workspace && out && sizes, B2J_E_ARG, "b2j_entropy_encode: null pointer");
     B2J_REQUIRE(zrl == B2J_ZRL_EAGER || zrl == B2J_ZRL_STANDARD, B2J_E_ARG, "b2j_entropy_encode: bad zrl policy %d", zrl);
-    B2J_REQUIRE(out_cap >= kHeaderBytes + 2, B2J_E_CAPACITY, "b2j_entropy_encode: out_cap %lld smaller than the header",
+    B2J_REQUIRE((opts & ~(0xFF | B2J_OPT_RESTART(0x7FFF))) == 0, B2J_E_ARG, "b2j_entropy_encode: unknown option bits 0x%x", opts);
+    B2J_REQUIRE(out_cap >= kHeaderMax + 2, B2J_E_CAPACITY, "b2j_entropy_encode: out_cap %lld smaller than the header",
                 (long long)out_cap);
     B2J_REQUIRE(((uintptr_t)coefs & 15) == 0 && ((uintptr_t)workspace & 255) == 0, B2J_E_ALIGN,
                 "b2j_entropy_encode: coefs must be 16-byte and workspace 256-byte aligned");
     Geo g;
     int rc = make_geo(desc, &g);
     if (rc) return rc;
-    const long long ucap = ucap_of(out_cap);
-    const int chunks = (int)((g.blocks_per_frame + kChunk - 1) / kChunk);
+    const SegPlan sp = seg_plan(g, out_cap, opts);
+    const long long nvf = (long long)g.n_frames * sp.nseg;
+    B2J_REQUIRE(nvf * sp.chunks < 0xFFFFFFFFLL && nvf < 0x7FFFFFFFLL, B2J_E_SHAPE,
+                "b2j_entropy_encode: %lld restart segments x %d chunks exceed the ticket range", nvf, sp.chunks);
+    const long long ucap = sp.ucap;
+    const int chunks = sp.chunks;
     uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
-    const FusedWs W = fused_ws(g, ucap);
+    const FusedWs W = fused_ws(g, sp);
     FusedEntropyParams P;
     P.coefs = coefs;
     P.ticket = reinterpret_cast<unsigned int *>(ws);
@@ -405,27 +448,31 @@ extern "C" int b2j_entropy_encode(const int16_t *coefs, const b2j_image_desc *de
     const size_t status_bytes = W.zero_bytes;
     P.ucap = ucap;
     P.chunks = chunks;
+    P.nseg = sp.nseg;
+    P.frame_blocks = g.blocks_per_frame;
     P.e = egeo_of(g);
+    P.e.nblk = sp.seg_blocks;
+    P.e.n_frames = (int)nvf;
     HeaderParam H;
     memset(&H, 0, sizeof H);
-    if (jfif_header(g, qy_host, qc_host, H.bytes) != kHeaderBytes) {
+    H.len = jfif_header(g, qy_host, qc_host, H.bytes, sp.ri);
+    if (H.len != kHeaderBytes + (sp.ri > 0 ? 6 : 0)) {
         set_error("b2j_entropy_encode: internal header length mismatch");
         return B2J_E_ARG;
     }
     const LutParam L = make_lut_param();
     cudaStream_t st = as_stream(stream);
     B2J_CUDA(cudaMemsetAsync(ws, 0, status_bytes, st));              // ticket, error flag, chunk status words
-    const long long total = (long long)chunks * g.n_frames;
+    const long long total = (long long)chunks * nvf;
     int dev = 0, sms = 148, per_sm = 1;
     B2J_CUDA(cudaGetDevice(&dev));
     B2J_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (zrl == B2J_ZRL_EAGER) {
-        B2J_CUDA(cudaFuncSetAttribute(k_entropy_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem));
-        B2J_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_entropy_fused<true>, kChunk, kFusedSmem));
-    } else {
-        B2J_CUDA(cudaFuncSetAttribute(k_entropy_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem));
-        B2J_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_entropy_fused<false>, kChunk, kFusedSmem));
-    }
+    using Kernel = void (*)(const FusedEntropyParams, const LutParam);
+    const bool seg = sp.nseg > 1;
+    const Kernel kernel = zrl == B2J_ZRL_EAGER ? (seg ? (Kernel)k_entropy_fused<true, true> : (Kernel)k_entropy_fused<true, false>)
+                                               : (seg ? (Kernel)k_entropy_fused<false, true> : (Kernel)k_entropy_fused<false, false>);
+    B2J_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem));
+    B2J_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kChunk, kFusedSmem));
     if (const char *cap = getenv("B2J_ENT_CTAS_PER_SM")) {              // tuning knob: leave room for a concurrent kernel
         const int c = atoi(cap);
         if (c >= 1 && c < per_sm) per_sm = c;
@@ -433,8 +480,8 @@ extern "C" int b2j_entropy_encode(const int16_t *coefs, const b2j_image_desc *de
     long long slots = (long long)sms * (per_sm < 1 ? 1 : per_sm);
     if (slots > kMaxSlots) slots = kMaxSlots;
     const unsigned grid = (unsigned)(total < slots ? total : slots);   // persistent CTAs, one scratch slot each
-    if (zrl == B2J_ZRL_EAGER) k_entropy_fused<true><<<grid, kChunk, kFusedSmem, st>>>(P, L);
-    else k_entropy_fused<false><<<grid, kChunk, kFusedSmem, st>>>(P, L);
+    kernel<<<grid, kChunk, kFusedSmem, st>>>(P, L);
     B2J_LAUNCH_CHECK("k_entropy_fused");
-    return launch_stuffing(P.unstuffed, P.total_bits, ffpart, sizes, out, ucap, out_cap, g.n_frames, H, P.error_flag, true, st);
+    return launch_stuffing(P.unstuffed, P.total_bits, ffpart, sizes, out, ucap, out_cap, g.n_frames, H, P.error_flag, true, st,
+                           sp.nseg);
 }

@@ -31,9 +31,12 @@ class JpegEncoder:
     zrl: "eager" (gateware run-length rule, rlecore.py:101-105) | "standard".
     dct: "model" (float64 model, the parity path) | "fixed" ([ext] the gateware's fixed-point DCT
     arithmetic, new_dct6.py:171-396 corrected; <= 4 LSB per coefficient from the model, not parity).
+    restart_interval: [ext] MCUs per restart interval (0 = none): DRI + RSTm markers, DC predictors
+    restart; the intervals are independent byte-aligned streams.
     """
 
-    def __init__(self, subsampling="444", quality=85, zrl="eager", tables=None, out_cap=None, dct="model"):
+    def __init__(self, subsampling="444", quality=85, zrl="eager", tables=None, out_cap=None, dct="model",
+                 restart_interval=0):
         if str(subsampling) not in _lib.SUB:
             raise ValueError("subsampling must be '444', '422' or '420'")
         if zrl not in _lib.ZRL:
@@ -43,6 +46,8 @@ class JpegEncoder:
         self.subsampling = str(subsampling)
         self.zrl = zrl
         self.dct = dct
+        self.restart_interval = int(restart_interval)
+        self._opts = _lib.ZRL[zrl] | _lib.DCT_MODE[dct] | _lib.opt_restart(restart_interval)
         if tables is not None:
             self.quality = 0
             self.qy, self.qc = [int(v) for v in tables[0]], [int(v) for v in tables[1]]
@@ -72,10 +77,10 @@ class JpegEncoder:
 
     def _workspace(self, desc, device):
         cap = self._cap(desc)
-        key = (desc.height, desc.width, desc.n_frames, cap, str(device))
+        key = (desc.height, desc.width, desc.n_frames, cap, str(device), self._opts)
         ws = self._ws.get(key)
         if ws is None:
-            nbytes = _lib.lib().b2j_encode_workspace_bytes(ctypes.byref(desc), cap)
+            nbytes = _lib.lib().b2j_encode_workspace_bytes_opts(ctypes.byref(desc), cap, self._opts)
             if nbytes == 0:
                 raise _lib.B2JError(-1, _lib.last_error())
             ws = torch.empty((nbytes,), dtype=torch.uint8, device=device)
@@ -113,7 +118,7 @@ class JpegEncoder:
             sizes = torch.empty((desc.n_frames,), dtype=torch.int64, device=rgb.device)
         with torch.cuda.device(rgb.device):
             _lib.check(_lib.lib().b2j_encode(rgb.data_ptr(), ctypes.byref(desc), self.quality, _lib.table_arg(self.qy),
-                                              _lib.table_arg(self.qc), _lib.ZRL[self.zrl] | _lib.DCT_MODE[self.dct], ws.data_ptr(),
+                                              _lib.table_arg(self.qc), self._opts, ws.data_ptr(),
                                               ws.numel(),
                                               out.data_ptr(), cap, sizes.data_ptr(), stream_ptr(stream)))
         return out, sizes
@@ -152,7 +157,7 @@ class JpegEncoder:
             d1 = _lib.make_desc(desc.height, desc.width, self.subsampling, fpc)
             if self.quality == 0:
                 raise ValueError("encode_host needs a quality (explicit tables are not supported on this path)")
-            _lib.check(_lib.lib().b2j_encoder_create(ctypes.byref(handle), ctypes.byref(d1), self.quality, _lib.ZRL[self.zrl] | _lib.DCT_MODE[self.dct],
+            _lib.check(_lib.lib().b2j_encoder_create(ctypes.byref(handle), ctypes.byref(d1), self.quality, self._opts,
                                                       cap, fpc))
             enc = handle
             self._host = {key: enc}

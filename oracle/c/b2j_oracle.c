@@ -414,18 +414,31 @@ int b2jo_block_bits(const int16_t *coefs, int height, int width, int sub, int zr
 int64_t b2jo_entropy_encode(const int16_t *coefs, int height, int width, int sub, int zrl,
                             uint8_t *out, int64_t cap, int64_t *total_bits)
 {
+    /* [ext] zrl >> 16 = restart interval in MCUs (T.81 B.2.4.4, E.1.4): every interval the byte is
+     * padded with 1s, RSTm (0xFFD0 + m mod 8) is written unstuffed, the DC predictors restart. */
+    const int ri = (zrl >> 16) & 0xFFFF;
+    zrl &= 0xFF;
     geo_t g;
     if (make_geo(height, width, sub, &g)) return -1;
     init_tables();
     bitw_t w = {out, out + cap, 0, 0, 0, 0};
     int pred[3] = {0, 0, 0};
-    for (int64_t m = 0; m < g.n_mcu; m++)
+    for (int64_t m = 0; m < g.n_mcu; m++) {
+        if (ri && m && m % ri == 0) {
+            if (w.n) { int pad = 8 - w.n; put_bits(&w, (1u << pad) - 1, pad); w.bits -= pad; }
+            if (w.p < w.end) *w.p = 0xFF; else w.overflow = 1;
+            w.p++;
+            if (w.p < w.end) *w.p = (uint8_t)(0xD0 + ((m / ri - 1) & 7)); else w.overflow = 1;
+            w.p++;
+            pred[0] = pred[1] = pred[2] = 0;
+        }
         for (int b = 0; b < g.bpm; b++) {
             int comp = b < g.h * g.v ? 0 : b - g.h * g.v + 1;
             const int16_t *c = coefs + (m * g.bpm + b) * 64;
             int diff = c[0] - pred[comp]; pred[comp] = c[0];
             encode_block(&w, c, diff, comp ? &T_DC_C : &T_DC_L, comp ? &T_AC_C : &T_AC_L, zrl);
         }
+    }
     if (total_bits) *total_bits = w.bits;
     if (w.n) { int pad = 8 - w.n; put_bits(&w, (1u << pad) - 1, pad); }
     return (int64_t)(w.p - out);
@@ -441,7 +454,16 @@ static uint8_t *seg(uint8_t *p, int marker, const uint8_t *payload, int n)
 }
 
 /* SOI APP0 DQT DQT SOF0 DHT x4 SOS; returns length (623 bytes). out >= 1024 B. */
+int b2jo_jfif_header_ex(int height, int width, int sub, const uint8_t *qy, const uint8_t *qc, int restart_interval,
+                        uint8_t *out);
 int b2jo_jfif_header(int height, int width, int sub, const uint8_t *qy, const uint8_t *qc, uint8_t *out)
+{
+    return b2jo_jfif_header_ex(height, width, sub, qy, qc, 0, out);
+}
+
+/* restart_interval > 0 adds a DRI segment in front of SOS (629 bytes) */
+int b2jo_jfif_header_ex(int height, int width, int sub, const uint8_t *qy, const uint8_t *qc, int restart_interval,
+                        uint8_t *out)
 {
     geo_t g;
     if (make_geo(height, width, sub, &g)) return -1;
@@ -469,17 +491,22 @@ int b2jo_jfif_header(int height, int width, int sub, const uint8_t *qy, const ui
             p = seg(p, 0xC4, buf, 17 + nv[t]);
         }
     }
+    if (restart_interval > 0) {
+        const uint8_t dri[2] = {(uint8_t)(restart_interval >> 8), (uint8_t)restart_interval};
+        p = seg(p, 0xDD, dri, 2);
+    }
     { const uint8_t sos[10] = {3, 1, 0x00, 2, 0x11, 3, 0x11, 0, 63, 0}; p = seg(p, 0xDA, sos, 10); }
     return (int)(p - out);
 }
 
 /* RGB -> JFIF file.  Returns bytes needed (> cap: truncated), < 0 on error.
- * zrl: 0 eager / 1 standard, optionally | 0x100 for the [ext] fixed-point DCT mode. */
+ * zrl: 0 eager / 1 standard, optionally | 0x100 for the [ext] fixed-point DCT mode,
+ * optionally | (restart interval in MCUs << 16). */
 int64_t b2jo_encode_jpeg(const uint8_t *rgb, int height, int width, int sub, int quality, int zrl,
                          uint8_t *out, int64_t cap)
 {
     const int dct_fixed = (zrl & 0x100) != 0;
-    zrl &= 0xFF;
+    zrl &= ~0x100;
     geo_t g;
     if (make_geo(height, width, sub, &g)) return -1;
     if (cap < 1024) return -2;
@@ -488,7 +515,7 @@ int64_t b2jo_encode_jpeg(const uint8_t *rgb, int height, int width, int sub, int
     int16_t *coefs = (int16_t *)malloc((size_t)g.n_mcu * g.bpm * 64 * sizeof(int16_t));
     if (!coefs) return -3;
     b2jo_encode_coefficients_ex(rgb, height, width, sub, qy, qc, dct_fixed, coefs);
-    int hl = b2jo_jfif_header(height, width, sub, qy, qc, out);
+    int hl = b2jo_jfif_header_ex(height, width, sub, qy, qc, (zrl >> 16) & 0xFFFF, out);
     int64_t n = b2jo_entropy_encode(coefs, height, width, sub, zrl, out + hl, cap - hl - 2 > 0 ? cap - hl - 2 : 0, NULL);
     free(coefs);
     int64_t total = hl + n + 2;
@@ -568,16 +595,24 @@ int b2jo_decode_coefficients(const uint8_t *jpg, int64_t n, int height, int widt
     init_tables();
     /* find SOS */
     int64_t pos = 2;
+    int ri = 0;
     while (pos + 4 <= n) {
         if (jpg[pos] != 0xFF) return 10;
         int m = jpg[pos + 1], ln = (jpg[pos + 2] << 8) | jpg[pos + 3];
+        if (m == 0xDD) ri = (jpg[pos + 4] << 8) | jpg[pos + 5];
         pos += 2 + ln;
         if (m == 0xDA) break;
     }
     bitr_t r = {jpg + pos, jpg + n, 0, 0, 0};
     int pred[3] = {0, 0, 0};
     memset(coefs, 0, (size_t)g.n_mcu * g.bpm * 64 * sizeof(int16_t));
-    for (int64_t m = 0; m < g.n_mcu; m++)
+    for (int64_t m = 0; m < g.n_mcu; m++) {
+        if (ri && m && m % ri == 0) {                       /* 1-padding, RSTm, predictors restart */
+            while (r.n) if (get_bit(&r) != 1) return 14;
+            if (r.p + 2 > r.end || r.p[0] != 0xFF || r.p[1] != 0xD0 + ((m / ri - 1) & 7)) return 15;
+            r.p += 2;
+            pred[0] = pred[1] = pred[2] = 0;
+        }
         for (int b = 0; b < g.bpm; b++) {
             int comp = b < g.h * g.v ? 0 : b - g.h * g.v + 1;
             int16_t *c = coefs + (m * g.bpm + b) * 64;
@@ -594,6 +629,7 @@ int b2jo_decode_coefficients(const uint8_t *jpg, int64_t n, int height, int widt
             }
             if (r.err) return r.err;
         }
+    }
     while (r.n) if (get_bit(&r) != 1) return 12;
     if (r.p + 2 > r.end || r.p[0] != 0xFF || r.p[1] != 0xD9) return 13;
     return 0;

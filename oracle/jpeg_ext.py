@@ -203,9 +203,10 @@ def _bit_length(a):
     return out
 
 
-def dc_differences(coefs, geo):
+def dc_differences(coefs, geo, restart_interval=0):
     """DC of every block minus DC of the previous block of the same component
-    in scan order (first block: minus 0)."""
+    in scan order (first block: minus 0).  [ext] restart_interval > 0: the
+    predictors restart from 0 every `restart_interval` MCUs (T.81 F.1.1.5.1 / E.1.4)."""
     nm, bpm, _ = coefs.shape
     comp = component_of_block(geo)
     dc = coefs[:, :, 0].astype(np.int64)
@@ -215,11 +216,15 @@ def dc_differences(coefs, geo):
         seq = dc[:, slots].reshape(-1)
         d = seq.copy()
         d[1:] = seq[1:] - seq[:-1]
-        diff[:, slots] = d.reshape(nm, len(slots))
+        d = d.reshape(nm, len(slots))
+        if restart_interval > 0:
+            first = np.arange(0, nm, restart_interval)
+            d[first, 0] = dc[first, slots[0]]                  # first block of the component in the interval
+        diff[:, slots] = d
     return diff
 
 
-def block_symbols(coefs, geo, zrl="eager"):
+def block_symbols(coefs, geo, zrl="eager", restart_interval=0):
     """Per coefficient position, the Huffman-coded bits it emits.
 
     Returns (value, nbits) uint64/int64 arrays of shape (nblk, 64, 2): slot 0 is
@@ -230,7 +235,7 @@ def block_symbols(coefs, geo, zrl="eager"):
     is_chroma = comp > 0
     c = coefs.reshape(-1, 64).astype(np.int64)
     nblk = c.shape[0]
-    diff = dc_differences(coefs, geo).reshape(-1)
+    diff = dc_differences(coefs, geo, restart_interval).reshape(-1)
     amp = c.copy()
     amp[:, 0] = diff
     size = _bit_length(np.abs(amp))
@@ -330,11 +335,28 @@ def stuff_bytes(data):
     return out
 
 
-def entropy_encode(coefs, geo, zrl="eager"):
-    """Scan data (stuffed, 1-padded) for coefficients in scan order."""
-    val, nb = block_symbols(coefs, geo, zrl)
-    packed, total_bits = pack_bits(val, nb)
-    return stuff_bytes(packed).tobytes(), total_bits
+def entropy_encode(coefs, geo, zrl="eager", restart_interval=0):
+    """Scan data (stuffed, 1-padded) for coefficients in scan order.
+
+    [ext] restart_interval > 0 (T.81 B.2.4.4, E.1.4): every `restart_interval` MCUs the current
+    byte is padded with 1s, a marker RSTm (0xFFD0 + m, m counting modulo 8) is written and the
+    DC predictors start again from 0; there is no marker after the last interval.  Returns the
+    scan bytes and the number of entropy-coded bits (padding and markers not counted)."""
+    val, nb = block_symbols(coefs, geo, zrl, restart_interval)
+    if restart_interval <= 0:
+        packed, total_bits = pack_bits(val, nb)
+        return stuff_bytes(packed).tobytes(), total_bits
+    nm, bpm = coefs.shape[0], coefs.shape[1]
+    val = val.reshape(nm, bpm, 64, 2)
+    nb = nb.reshape(nm, bpm, 64, 2)
+    out, total_bits = b"", 0
+    for k, m0 in enumerate(range(0, nm, restart_interval)):
+        packed, bits = pack_bits(val[m0:m0 + restart_interval], nb[m0:m0 + restart_interval])
+        total_bits += bits
+        if k:
+            out += bytes([0xFF, 0xD0 + ((k - 1) & 7)])
+        out += stuff_bytes(packed).tobytes()
+    return out, total_bits
 
 
 # ---------------------------------------------------------------- container
@@ -343,8 +365,8 @@ def _seg(marker, payload):
     return struct.pack(">BBH", 0xFF, marker, len(payload) + 2) + payload
 
 
-def jfif_header(height, width, subsampling, qy, qc):
-    """SOI, APP0(JFIF 1.01), DQT x2 (zig-zag order), SOF0, DHT x4, SOS."""
+def jfif_header(height, width, subsampling, qy, qc, restart_interval=0):
+    """SOI, APP0(JFIF 1.01), DQT x2 (zig-zag order), SOF0, DHT x4, [DRI,] SOS."""
     h, v = SUBSAMPLING[subsampling]
     out = b"\xFF\xD8"
     out += _seg(0xE0, b"JFIF\x00" + bytes([1, 1, 0]) + struct.pack(">HH", 1, 1) + bytes([0, 0]))
@@ -355,16 +377,20 @@ def jfif_header(height, width, subsampling, qy, qc):
                 bytes([1, (h << 4) | v, 0, 2, 0x11, 1, 3, 0x11, 1]))
     for tc_th, tab in ((0x00, DC_LUMA), (0x10, AC_LUMA), (0x01, DC_CHROMA), (0x11, AC_CHROMA)):
         out += _seg(0xC4, bytes([tc_th]) + bytes(tab[0]) + bytes(tab[1]))
+    if restart_interval > 0:
+        out += _seg(0xDD, struct.pack(">H", restart_interval))
     out += _seg(0xDA, bytes([3, 1, 0x00, 2, 0x11, 3, 0x11, 0, 63, 0]))
     return out
 
 
-def encode_jpeg(rgb, subsampling="444", quality=85, zrl="eager"):
+def encode_jpeg(rgb, subsampling="444", quality=85, zrl="eager", restart_interval=0):
     """Full RGB -> JFIF bytes."""
+    if not 0 <= restart_interval <= 65535:
+        raise ValueError("restart_interval must be in 0..65535")
     qy, qc = quant_tables(quality)
     coefs, geo = encode_coefficients(rgb, subsampling, qy, qc)
-    scan, _ = entropy_encode(coefs, geo, zrl)
-    return jfif_header(rgb.shape[0], rgb.shape[1], subsampling, qy, qc) + scan + b"\xFF\xD9"
+    scan, _ = entropy_encode(coefs, geo, zrl, restart_interval)
+    return jfif_header(rgb.shape[0], rgb.shape[1], subsampling, qy, qc, restart_interval) + scan + b"\xFF\xD9"
 
 
 # ---------------------------------------------------------------- decoder
@@ -375,6 +401,13 @@ class _BitReader:
         self.pos = 0
         self.acc = 0
         self.n = 0
+
+    def restart(self, expect):
+        """Discard the 1-padding of the current byte and consume the marker RST<expect>."""
+        while self.n:
+            assert self.bit() == 1, "non-1 padding before a restart marker"
+        assert self.data[self.pos] == 0xFF and self.data[self.pos + 1] == 0xD0 + expect, "missing RST%d" % expect
+        self.pos += 2
 
     def bit(self):
         if self.n == 0:
@@ -411,6 +444,7 @@ def decode_jpeg_coefficients(data):
     qt = {}
     ht = {}
     frame = None
+    restart_interval = 0
     while True:
         assert data[pos] == 0xFF, "expected marker at %d" % pos
         m = data[pos + 1]
@@ -439,6 +473,8 @@ def decode_jpeg_coefficients(data):
             frame = dict(height=hgt, width=wid,
                          comps=[(seg[6 + 3 * k], seg[7 + 3 * k] >> 4, seg[7 + 3 * k] & 15, seg[8 + 3 * k])
                                 for k in range(3)])
+        elif m == 0xDD:
+            restart_interval = struct.unpack(">H", seg[:2])[0]
         elif m == 0xDA:
             break
     h, v = frame["comps"][0][1], frame["comps"][0][2]
@@ -463,6 +499,9 @@ def decode_jpeg_coefficients(data):
         return vv if s == 0 or vv >= (1 << (s - 1)) else vv - (1 << s) + 1
 
     for mcu in range(geo["n_mcu"]):
+        if restart_interval and mcu and mcu % restart_interval == 0:
+            rd.restart((mcu // restart_interval - 1) & 7)
+            pred = [0, 0, 0]
         for b in range(geo["blocks_per_mcu"]):
             c = int(comp[b])
             dct, act = (ht[0x00], ht[0x10]) if c == 0 else (ht[0x01], ht[0x11])
@@ -487,4 +526,4 @@ def decode_jpeg_coefficients(data):
     tail = data[pos + rd.pos:]
     assert tail[:2] == b"\xFF\xD9", "missing EOI"
     return dict(height=frame["height"], width=frame["width"], subsampling=sub,
-                qy=qt[0], qc=qt[1], coefs=coefs, geo=geo)
+                qy=qt[0], qc=qt[1], coefs=coefs, geo=geo, restart_interval=restart_interval)

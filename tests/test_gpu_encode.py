@@ -284,3 +284,46 @@ def test_fixed_dct_mode_equals_its_oracle(lj, oracle_c, sub):
     out_h, sizes_h = host.encode_host(frames)
     assert bytes(out_h[1, :int(sizes_h[1])].numpy().tobytes()) == files[1]
     host.close()
+
+
+@pytest.mark.parametrize("sub", SUBS)
+def test_restart_intervals_bytes_equal_oracle(lj, oracle_c, sub):
+    """[ext] restart intervals: DRI + RSTm, predictors restart, every interval an independent
+    byte-aligned stream.  Bytes equal the oracle for short, ragged, row-sized and oversized intervals."""
+    s = synth(lj)
+    h, w = 72, 200
+    frames = torch.stack([s.frame(h, w, 13, i, kind) for i, kind in enumerate(("photo", "noise", "grey"))])
+    g = oracle_c.geometry(h, w, sub)
+    n_mcu, mcus_x = g["n_mcu"], g["mcus_x"]
+    for zi, zrl in enumerate(("eager", "standard")):
+        for ri in (1, 5, mcus_x, 2 * mcus_x + 3, n_mcu - 1, n_mcu, 30000):
+            enc = lj.JpegEncoder(sub, quality=80, zrl=zrl, restart_interval=ri, out_cap=h * w * 8)
+            files = enc.encode(frames.cuda())
+            for i, f in enumerate(files):
+                assert f == oracle_c.encode_jpeg(frames[i].numpy(), sub, 80, zi | (ri << 16)), (zrl, ri, i)
+
+
+def test_restart_intervals_full_size_and_host_path(lj, oracle_c):
+    """1080p 4:2:0 with one interval per MCU row (120 MCUs): 68 segments per frame, through the
+    device path, the host-buffer encoder and together with dct="fixed"; libjpeg decodes the file
+    to the same pixels as the file without restart markers."""
+    import io as _io
+    from PIL import Image
+    s = synth(lj)
+    frames = torch.stack([s.frame(1080, 1920, 2, i) for i in range(3)])
+    enc = lj.JpegEncoder("420", quality=75, zrl="standard", restart_interval=120)
+    files = enc.encode(frames.cuda())
+    plain = lj.JpegEncoder("420", quality=75, zrl="standard").encode(frames[:1].cuda())[0]
+    for i in range(3):
+        assert files[i] == oracle_c.encode_jpeg(frames[i].numpy(), "420", 75, 1 | (120 << 16)), i
+    a = np.asarray(Image.open(_io.BytesIO(files[0])).convert("RGB"))
+    b = np.asarray(Image.open(_io.BytesIO(plain)).convert("RGB"))
+    assert np.array_equal(a, b)
+    out_h, sizes_h = enc.encode_host(frames, frames_per_chunk=2)
+    for i in range(3):
+        assert bytes(out_h[i, :int(sizes_h[i])].numpy().tobytes()) == files[i]
+    enc.close()
+    fx = lj.JpegEncoder("420", quality=75, zrl="eager", dct="fixed", restart_interval=7)
+    assert fx.encode(frames[:1].cuda())[0] == oracle_c.encode_jpeg(frames[0].numpy(), "420", 75, 0 | 0x100 | (7 << 16))
+    with pytest.raises(ValueError):
+        lj.JpegEncoder("420", restart_interval=40000)

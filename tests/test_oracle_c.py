@@ -94,3 +94,33 @@ def test_fixed_dct_mode_c_equals_numpy_and_stays_near_the_model(oracle_c, golden
     assert dev.max() <= 4 and dev.mean() < 1.0
     assert f[-3, 0] == -1024 and f[-2, 0] == 1016 and not f[-1].any()      # flat blocks: exact DC, no AC
     assert not f[-3, 1:].any() and not f[-2, 1:].any()
+
+
+def test_restart_intervals_c_equals_numpy_and_libjpeg_decodes_them(oracle_c):
+    """[ext] restart intervals (T.81 B.2.4.4, E.1.4).  No reference counterpart, so
+    the pin is threefold: the two restatements agree byte for byte; both baseline decoders of
+    oracle/ recover the same coefficients as from the file without restarts; and libjpeg (PIL)
+    decodes every file to exactly the pixels of the file without restarts."""
+    import io
+    from PIL import Image
+    from oracle import jpeg_ext as J
+    rng = np.random.default_rng(5)
+    img = np.clip(np.add.outer(np.arange(40) * 5, np.arange(72) * 2)[..., None] + rng.integers(-20, 20, (40, 72, 3)),
+                  0, 255).astype(np.uint8)
+    for sub in ("444", "422", "420"):
+        plain = J.encode_jpeg(img, sub, 75, "standard")
+        ref_px = np.asarray(Image.open(io.BytesIO(plain)).convert("RGB"))
+        ref_coefs = J.decode_jpeg_coefficients(plain)["coefs"]
+        n_mcu = J.geometry(40, 72, sub)["n_mcu"]
+        for zi, zrl in enumerate(("eager", "standard")):
+            for ri in (1, 2, 3, 9, n_mcu - 1, n_mcu, 1000):
+                a = J.encode_jpeg(img, sub, 75, zrl, ri)
+                assert a == oracle_c.encode_jpeg(img, sub, 75, zi | (ri << 16)), (sub, zrl, ri)
+                n_markers = sum(a.count(bytes([0xFF, 0xD0 + m])) for m in range(8))
+                assert n_markers >= (n_mcu - 1) // ri                      # (entropy bytes are stuffed, so >= is exact enough)
+                d = J.decode_jpeg_coefficients(a)
+                assert d["restart_interval"] == ri and np.array_equal(d["coefs"], ref_coefs)
+                rc, co = oracle_c.decode_coefficients(a, 40, 72, sub)
+                assert rc == 0 and np.array_equal(co, ref_coefs)
+                if zrl == "standard":
+                    assert np.array_equal(np.asarray(Image.open(io.BytesIO(a)).convert("RGB")), ref_px)
