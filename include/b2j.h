@@ -68,12 +68,16 @@ extern "C" {
 /* The `zrl` argument of b2j_entropy_encode, b2j_encode and b2j_encoder_create is an option word:
  *   bits 0..7    B2J_ZRL_*
  *   bit  8       B2J_OPT_DCT_FIXED (b2j_encode / b2j_encoder_create: K1 uses B2J_FUSED_DCT_FIXED)
+ *   bits 12..14  B2J_OPT_RST_PHASE(p): the first restart marker written is RSTp instead of RST0
+ *                (a band of a larger frame, encoded on its own: see INTEGRATION.md "one frame on
+ *                several GPUs")
  *   bits 16..30  B2J_OPT_RESTART(n): [ext] restart interval of n MCUs, 1..32767 (T.81 B.2.4.4,
  *                E.1.4; the reference has no counterpart): a DRI segment in the
  *                header, and every n MCUs the byte is padded with 1s, RSTm (0xFFD0 + m mod 8)
  *                is written and the DC predictors restart from 0.  Workspaces must then be
  *                sized with the *_workspace_bytes_opts() queries. */
 #define B2J_OPT_DCT_FIXED 0x100
+#define B2J_OPT_RST_PHASE(p) (((int)(p) & 7) << 12)
 #define B2J_OPT_RESTART(n) ((int)(n) << 16)
 
 /* A batch of equally sized, interleaved 8-bit RGB frames (H x W x 3, like the

@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(256) k_ff_scan(uint32_t *__restrict__ ffpart, 
 __global__ void __launch_bounds__(256) k_stuff_write(const uint8_t *__restrict__ unstuffed, const int64_t *__restrict__ total_bits,
                                                      const uint32_t *__restrict__ ffpart, const uint32_t *__restrict__ segbase,
                                                      const int64_t *__restrict__ sizes, uint8_t *__restrict__ out, long long ucap,
-                                                     long long out_cap, int chunks, int nseg,
+                                                     long long out_cap, int chunks, int nseg, int rst_phase,
                                                      const __grid_constant__ HeaderParam H)
 {
     __shared__ uint32_t s_warp[8];
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(256) k_stuff_write(const uint8_t *__restrict__
         // the marker after the segment's last chunk: RSTm (T.81 B.2.4.4 / E.1.4), or EOI after the last segment
         if ((long long)(ch + 1) * kStuffChunk >= nbytes && threadIdx.x == 0) {
             dst[n_out] = 0xFF;
-            dst[n_out + 1] = seg == nseg - 1 ? 0xD9 : (uint8_t)(0xD0 + (seg & 7));
+            dst[n_out + 1] = seg == nseg - 1 ? 0xD9 : (uint8_t)(0xD0 + ((seg + rst_phase) & 7));
         }
         __syncthreads();                                            // s_out and s_warp are reused by the next chunk
     }
@@ -362,7 +362,7 @@ static int scan_chunks(long long nblk) { return (int)((nblk + kScanChunk - 1) / 
 
 int launch_stuffing(const uint8_t *unstuffed, const int64_t *total_bits, uint32_t *ffpart, int64_t *sizes, uint8_t *out,
                     long long ucap, long long out_cap, int n_frames, const HeaderParam &H, const int *error_flag,
-                    bool counted, cudaStream_t st, int nseg)
+                    bool counted, cudaStream_t st, int nseg, int rst_phase)
 {
     const int schunks = stuff_chunks(ucap);
     const long long nvf = (long long)n_frames * nseg;
@@ -380,7 +380,7 @@ int launch_stuffing(const uint8_t *unstuffed, const int64_t *total_bits, uint32_
     if (per_seg > schunks) per_seg = schunks;
     if (per_seg < 1) per_seg = 1;
     k_stuff_write<<<dim3((unsigned)nvf, (unsigned)per_seg), 256, 0, st>>>(unstuffed, total_bits, ffpart, segbase, sizes, out, ucap,
-                                                                          out_cap, schunks, nseg, H);
+                                                                          out_cap, schunks, nseg, rst_phase, H);
     B2J_LAUNCH_CHECK("k_stuff_write");
     return B2J_OK;
 }

@@ -137,9 +137,9 @@ static inline int stuff_chunks(long long ucap) { return (int)((ucap + kStuffChun
 // counts while it composes the words), so the counting pass is skipped.
 // nseg > 1 ([ext] restart intervals): every frame is nseg consecutive, independently packed
 // streams ("segments": ucap, total_bits and ffpart are per segment, n_frames * nseg of them); they
-// are joined with RSTm markers between them.
+// are joined with RSTm markers between them, m = (segment + rst_phase) mod 8.
 int launch_stuffing(const uint8_t *unstuffed, const int64_t *total_bits, uint32_t *ffpart, int64_t *sizes, uint8_t *out,
                     long long ucap, long long out_cap, int n_frames, const HeaderParam &H, const int *error_flag,
-                    bool counted, cudaStream_t st, int nseg = 1);
+                    bool counted, cudaStream_t st, int nseg = 1, int rst_phase = 0);
 
 }  // namespace b2j

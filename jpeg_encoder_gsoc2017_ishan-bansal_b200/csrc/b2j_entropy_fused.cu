@@ -418,7 +418,8 @@ extern "C" int b2j_entropy_encode(const int16_t *coefs, const b2j_image_desc *de
     const int zrl = opts & 0xFF;
     B2J_REQUIRE(coefs && qy_host && qc_host && workspace && out && sizes, B2J_E_ARG, "b2j_entropy_encode: null pointer");
     B2J_REQUIRE(zrl == B2J_ZRL_EAGER || zrl == B2J_ZRL_STANDARD, B2J_E_ARG, "b2j_entropy_encode: bad zrl policy %d", zrl);
-    B2J_REQUIRE((opts & ~(0xFF | B2J_OPT_RESTART(0x7FFF))) == 0, B2J_E_ARG, "b2j_entropy_encode: unknown option bits 0x%x", opts);
+    B2J_REQUIRE((opts & ~(0xFF | B2J_OPT_RST_PHASE(7) | B2J_OPT_RESTART(0x7FFF))) == 0, B2J_E_ARG,
+                "b2j_entropy_encode: unknown option bits 0x%x", opts);
     B2J_REQUIRE(out_cap >= kHeaderMax + 2, B2J_E_CAPACITY, "b2j_entropy_encode: out_cap %lld smaller than the header",
                 (long long)out_cap);
     B2J_REQUIRE(((uintptr_t)coefs & 15) == 0 && ((uintptr_t)workspace & 255) == 0, B2J_E_ALIGN,
@@ -483,5 +484,5 @@ extern "C" int b2j_entropy_encode(const int16_t *coefs, const b2j_image_desc *de
     kernel<<<grid, kChunk, kFusedSmem, st>>>(P, L);
     B2J_LAUNCH_CHECK("k_entropy_fused");
     return launch_stuffing(P.unstuffed, P.total_bits, ffpart, sizes, out, ucap, out_cap, g.n_frames, H, P.error_flag, true, st,
-                           sp.nseg);
+                           sp.nseg, (opts >> 12) & 7);
 }

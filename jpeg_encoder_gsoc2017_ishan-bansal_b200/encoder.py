@@ -23,6 +23,63 @@ def shard_range(n_frames, world_size, rank):
     return (n_frames * rank) // world_size, (n_frames * (rank + 1)) // world_size
 
 
+MCU_HEIGHT = {"444": 8, "422": 8, "420": 16}
+
+
+def band_plan(height, subsampling, n_bands):
+    """[ext] Splits one frame into `n_bands` horizontal bands of whole MCU rows, so that the bands can
+    be encoded independently (on different GPUs) with one restart interval per MCU row and joined
+    into ONE baseline JPEG.  Returns a list of (y0, y1, mcu_rows_before) with
+    pixel rows [y0, y1); bands that would be empty are dropped."""
+    mh = MCU_HEIGHT[str(subsampling)]
+    rows = (int(height) + mh - 1) // mh
+    n_bands = max(1, min(int(n_bands), rows))
+    out = []
+    for b in range(n_bands):
+        r0, r1 = rows * b // n_bands, rows * (b + 1) // n_bands
+        if r1 > r0:
+            out.append((r0 * mh, min(r1 * mh, int(height)), r0))
+    return out
+
+
+def _header_end(jpg):
+    """Offset of the first scan byte: walks the marker segments up to and including SOS."""
+    pos = 2
+    while True:
+        if jpg[pos] != 0xFF:
+            raise ValueError("bad JPEG marker structure")
+        marker, ln = jpg[pos + 1], (jpg[pos + 2] << 8) | jpg[pos + 3]
+        pos += 2 + ln
+        if marker == 0xDA:
+            return pos
+
+
+def assemble_bands(band_files, plan, height):
+    """Joins the JFIF files of the bands of `band_plan` (each encoded with restart_interval = one
+    MCU row and restart marker phase = mcu_rows_before % 8) into the file of the whole frame: the
+    first band's header with the frame's height, then every band's scan with an RSTm marker in
+    place of the band's EOI, m continuing the count of MCU rows modulo 8."""
+    if len(band_files) != len(plan):
+        raise ValueError("need one file per band")
+    first = bytes(band_files[0])
+    end = _header_end(first)
+    header = bytearray(first[:end])
+    sof = header.find(b"\xFF\xC0")
+    header[sof + 5] = (int(height) >> 8) & 0xFF                 # SOF0: Lf(2) P(1) Y(2) X(2)
+    header[sof + 6] = int(height) & 0xFF
+    parts = [bytes(header)]
+    for i, (f, (y0, y1, before)) in enumerate(zip(band_files, plan)):
+        f = bytes(f)
+        if f[-2:] != b"\xFF\xD9":
+            raise ValueError("band %d does not end with EOI" % i)
+        parts.append(f[_header_end(f):-2])
+        if i + 1 < len(plan):
+            rows_so_far = plan[i + 1][2]
+            parts.append(bytes([0xFF, 0xD0 + ((rows_so_far - 1) & 7)]))
+    parts.append(b"\xFF\xD9")
+    return b"".join(parts)
+
+
 class JpegEncoder:
     """RGB frames -> baseline JFIF files on one GPU.
 
@@ -134,6 +191,30 @@ class JpegEncoder:
         host = out.cpu()
         return [bytes(host[i, :int(sizes[i])].numpy().tobytes()) for i in range(out.shape[0])]
 
+    def band_encoder(self, width, mcu_rows_before):
+        """The encoder for one band of `band_plan`: same tables and policies, one restart interval
+        per MCU row, restart markers counted from the band's position in the frame."""
+        if self.restart_interval:
+            raise ValueError("band splitting chooses the restart interval itself")
+        mcus_x = _lib.geometry(_lib.make_desc(8, width, self.subsampling, 1)).mcus_x
+        enc = JpegEncoder(self.subsampling, quality=self.quality or 85, zrl=self.zrl, dct=self.dct, restart_interval=mcus_x,
+                          tables=None if self.quality else (self.qy, self.qc), out_cap=self.out_cap)
+        enc._opts |= (int(mcu_rows_before) & 7) << 12            # B2J_OPT_RST_PHASE
+        return enc
+
+    def encode_frame_bands(self, rgb, n_bands):
+        """[ext] One frame (H, W, 3) encoded as `n_bands` independent bands on this GPU and joined:
+        byte-identical to encoding the whole frame with restart_interval = MCUs per row.  The
+        multi-GPU form is ShardedJpegEncoder.encode_frame_split."""
+        if rgb.dim() != 3:
+            raise ValueError("encode_frame_bands takes one frame (H, W, 3)")
+        h, w = rgb.shape[0], rgb.shape[1]
+        plan = band_plan(h, self.subsampling, n_bands)
+        files = []
+        for (y0, y1, before) in plan:
+            files.append(self.band_encoder(w, before).encode(rgb[y0:y1][None])[0])
+        return assemble_bands(files, plan, h)
+
     def launch_count(self, desc):
         return int(_lib.lib().b2j_encode_launch_count(ctypes.byref(desc)))
 
@@ -223,6 +304,24 @@ class ShardedJpegEncoder:
 
     def local_range(self, n_frames):
         return shard_range(n_frames, self.world_size, self.rank)
+
+    def encode_frame_split(self, rgb_frame, dst=0, group=None):
+        """[ext] ONE frame across all ranks (a single 8K frame cannot use 8 GPUs without
+        restart markers): rank r encodes band r of band_plan(H, subsampling, world_size) on its
+        GPU; the finished band files are gathered on `dst` (output only, no collective on the data
+        path) and joined into one baseline JPEG.  Returns the file on `dst`, None elsewhere."""
+        import torch.distributed as dist
+        h, w = rgb_frame.shape[0], rgb_frame.shape[1]
+        plan = band_plan(h, self.encoder.subsampling, self.world_size)
+        mine = None
+        if self.rank < len(plan):
+            y0, y1, before = plan[self.rank]
+            mine = self.encoder.band_encoder(w, before).encode(rgb_frame[y0:y1][None])[0]
+        gathered = [None] * self.world_size if dist.get_rank(group) == dst else None
+        dist.gather_object(mine, gathered, dst=dst, group=group)
+        if gathered is None:
+            return None
+        return assemble_bands([g for g in gathered if g is not None], plan, h)
 
     def encode_local(self, rgb_all_or_local, n_frames=None, already_local=False):
         """Encodes this rank's shard on its GPU; returns (out, sizes) device tensors of the shard."""

@@ -327,3 +327,18 @@ def test_restart_intervals_full_size_and_host_path(lj, oracle_c):
     assert fx.encode(frames[:1].cuda())[0] == oracle_c.encode_jpeg(frames[0].numpy(), "420", 75, 0 | 0x100 | (7 << 16))
     with pytest.raises(ValueError):
         lj.JpegEncoder("420", restart_interval=40000)
+
+
+@pytest.mark.parametrize("sub", SUBS)
+def test_one_frame_encoded_as_bands_equals_the_whole_frame(lj, oracle_c, sub):
+    """[ext] a frame split into bands of whole MCU rows (the unit one GPU would take), each band
+    encoded on its own with the right restart-marker phase, joined into one file: byte-identical
+    to the whole frame with one restart interval per MCU row."""
+    s = synth(lj)
+    for (h, w) in ((203, 328), (1080, 1920)):
+        frame = s.frame(h, w, 17, 0)
+        mcus_x = oracle_c.geometry(h, w, sub)["mcus_x"]
+        whole = oracle_c.encode_jpeg(frame.numpy(), sub, 75, 0 | (mcus_x << 16))
+        enc = lj.JpegEncoder(sub, quality=75)
+        for n_bands in ((1, 2, 3, 5, 8) if h < 1000 else (8,)):
+            assert enc.encode_frame_bands(frame.cuda(), n_bands) == whole, (h, w, n_bands)
