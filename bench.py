@@ -358,7 +358,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": px_per_step * e_steps / dt / 1e6, "unit": UNIT,
-               "h2d_bytes_per_step": n_gpus * frames * H * W * 3, "d2h_bytes_per_step": n_gpus * (frames * cap + frames * 8),
+               "h2d_bytes_per_step": n_gpus * frames * H * W * 3, "d2h_bytes_per_step": n_gpus * (out_bytes + frames * 8),
                "steps": e_steps, "ms_per_step": dt / e_steps * 1e3, "frames_per_chunk": fpc,
                "api": "b2j_encoder_encode_host (pinned host RGB in, JFIF bytes in pinned host memory out; wall clock "
                       "around the call, which returns when the last byte is on the host)"}

@@ -174,18 +174,28 @@ static bool is_pinned(const void *p)
     return a.type == cudaMemoryTypeHost;
 }
 
-// Gathers slot `s` (whose D2H copies have completed) into the caller's buffers.
+// Finishes the chunk held by slot `s`: once its sizes are on the host, only the bytes every frame
+// really has are copied back (a slot is several times larger than a typical file), straight into
+// the caller's buffer when that is pinned.  Runs while the other slot's H2D copy and kernels are
+// in flight, so the D2H traffic overlaps them.
 static int drain_slot(b2j_encoder *e, int s, int first_frame, int n, uint8_t *out_host, int64_t *sizes_host, bool out_pinned,
                       int *bad)
 {
-    B2J_CUDA(cudaStreamSynchronize(e->stream[s]));
+    B2J_CUDA(cudaStreamSynchronize(e->stream[s]));                  // kernels done, sizes on the host
     for (int i = 0; i < n; i++) {
         const int64_t sz = e->h_sizes[s][i];
         sizes_host[first_frame + i] = sz;
         if (sz < 0) { *bad = 1; continue; }
-        if (!out_pinned)
-            memcpy(out_host + (size_t)(first_frame + i) * (size_t)e->out_cap, e->h_out[s] + (size_t)i * (size_t)e->out_cap, (size_t)sz);
+        uint8_t *dst = out_pinned ? out_host + (size_t)(first_frame + i) * (size_t)e->out_cap : e->h_out[s] + (size_t)i * (size_t)e->out_cap;
+        B2J_CUDA(cudaMemcpyAsync(dst, e->d_out[s] + (size_t)i * (size_t)e->out_cap, (size_t)sz, cudaMemcpyDeviceToHost, e->stream[s]));
     }
+    B2J_CUDA(cudaStreamSynchronize(e->stream[s]));
+    if (!out_pinned)
+        for (int i = 0; i < n; i++) {
+            const int64_t sz = e->h_sizes[s][i];
+            if (sz > 0)
+                memcpy(out_host + (size_t)(first_frame + i) * (size_t)e->out_cap, e->h_out[s] + (size_t)i * (size_t)e->out_cap, (size_t)sz);
+        }
     return B2J_OK;
 }
 
@@ -221,10 +231,7 @@ extern "C" int b2j_encoder_encode_host(b2j_encoder *enc, const uint8_t *rgb_host
                             e->out_cap, e->d_sizes[s], e->stream[s]);
         if (rc) return rc;
         B2J_CUDA(cudaMemcpyAsync(e->h_sizes[s], e->d_sizes[s], sizeof(int64_t) * n, cudaMemcpyDeviceToHost, e->stream[s]));
-        // the sizes are not known on the host yet, so the D2H copy takes whole slots;
-        // for JPEG-sized slots this stays far below the input traffic
-        uint8_t *dst = out_pinned ? out_host + (size_t)first * (size_t)e->out_cap : e->h_out[s];
-        B2J_CUDA(cudaMemcpyAsync(dst, e->d_out[s], (size_t)n * (size_t)e->out_cap, cudaMemcpyDeviceToHost, e->stream[s]));
+        // the file bytes follow in drain_slot(), once the sizes are known on the host
         pend_first[s] = first;
         pend_n[s] = n;
     }
