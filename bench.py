@@ -222,6 +222,28 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------- GPU arm
+def bind_to_gpu_numa_node(nvml_index):
+    """Pins this rank to the CPUs NVML reports as local to its GPU, so that the pinned host buffers
+    (first touch) and the H2D/D2H copies stay on the GPU's own socket.  Returns the previous
+    affinity (restored for the CPU-baseline leg, which must use all host threads)."""
+    try:
+        before = os.sched_getaffinity(0)
+    except AttributeError:
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(nvml_index))
+        n_words = (max(before) + 64) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1} & before
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+    return before
+
+
 def _nvml_index(torch, cuda_index):
     """NVML enumerates physical GPUs; CUDA_VISIBLE_DEVICES may renumber them."""
     vis = os.environ.get("CUDA_VISIBLE_DEVICES")
@@ -250,6 +272,7 @@ def main():
         raise RuntimeError("bench.py needs a CUDA device: the encode path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    all_cpus = bind_to_gpu_numa_node(_nvml_index(torch, local_rank))   # before the pinned buffers are allocated
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = max(world, 1)
@@ -402,6 +425,8 @@ def main():
                         "other instructions per 8x8 block-equivalent (DESIGN.md)"}
 
     base = None
+    if all_cpus:
+        os.sched_setaffinity(0, all_cpus)            # the CPU leg uses every host thread
     if not args.skip_cpu_baseline and n_gpus == 1 and args.dct == "model" and not args.restart:        # reported on rank 0 at N = 1 only
         base, _ = cpu_baseline(host, 2)
 
