@@ -67,6 +67,9 @@ def parse():
     ap.add_argument("--config", default="2", choices=sorted(PRESETS), help="BASELINE.json config (default 2, the headline)")
     ap.add_argument("--dct", default="model", choices=["model", "fixed"],
                     help="model = float64 model arithmetic (parity path, the headline); fixed = [ext] gateware fixed point, non-parity")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay the step from a CUDA graph (for the launch-bound single-frame config; stage times come "
+                         "from an untimed ungraphed pass)")
     ap.add_argument("--restart", type=int, default=0, help="[ext] restart interval in MCUs (0 = none, the headline)")
     ap.add_argument("--kind", default="photo", choices=["photo", "noise", "grey"], help="synthetic content (SURVEY 8d stress)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
@@ -80,6 +83,8 @@ def parse():
     UNIQUE_FRAMES = max(1, min(UNIQUE_FRAMES, (32 * 1080 * 1920) // (H * W)))     # bound the host-side generation time
     if KIND != "photo":
         WORKLOAD += " [content: %s]" % KIND
+    if args.graph:
+        WORKLOAD += " [step replayed from a CUDA graph]"
     if args.dct != "model":
         WORKLOAD += " [dct: %s, NON-PARITY arithmetic mode]" % args.dct
     if args.restart:
@@ -306,6 +311,7 @@ def main():
 
     def step(ev=None):
         """One pass of the hot path: exactly the launches b2j_encode issues, with optional stage events."""
+        nonlocal stream, sp
         if ev: ev[0].record(stream)
         lj._lib.check(L.b2j_fused_block(rgb.data_ptr(), dref, qy_a, qc_a, coefs.data_ptr(), dct_flag, sp))
         if ev: ev[1].record(stream)
@@ -336,13 +342,32 @@ def main():
         step()
     sampler = ClockSampler(_nvml_index(torch, local_rank if world > 1 else torch.cuda.current_device())) if rank == 0 else None
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    graph = None
+    if args.graph:
+        for k in range(args.steps):                 # stage split from an ungraphed pass (not part of `value`)
+            step(evs[k])
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            sp_saved, stream_saved = sp, stream
+            stream = side
+            sp = side.cuda_stream
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                step()
+            stream, sp = stream_saved, sp_saved
+        for _ in range(args.warmup):
+            graph.replay()
     barrier()
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     w0 = time.perf_counter()
     t_start.record(stream)
     for k in range(args.steps):
-        step(evs[k])
+        if graph is not None:
+            graph.replay()
+        else:
+            step(evs[k])
     t_end.record(stream)
     barrier()
     if sampler:

@@ -342,3 +342,23 @@ def test_one_frame_encoded_as_bands_equals_the_whole_frame(lj, oracle_c, sub):
         enc = lj.JpegEncoder(sub, quality=75)
         for n_bands in ((1, 2, 3, 5, 8) if h < 1000 else (8,)):
             assert enc.encode_frame_bands(frame.cuda(), n_bands) == whole, (h, w, n_bands)
+
+
+def test_encode_is_cuda_graph_capturable(lj, oracle_c):
+    """The whole path (memset + 4 kernels) only enqueues work on the caller's stream, so it can be
+    captured once into a CUDA graph and replayed per frame (the launch-bound single-frame case)."""
+    s = synth(lj)
+    frames = [s.frame(360, 640, 19, i) for i in range(3)]
+    enc = lj.JpegEncoder("420", quality=75)
+    rgb = frames[0].cuda()[None].clone()
+    out, sizes = enc.encode_device(rgb)                     # warm-up outside the capture (workspace allocation)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        enc.encode_device(rgb, out=out, sizes=sizes, stream=torch.cuda.current_stream())
+    for f in frames:
+        rgb.copy_(f.cuda()[None])
+        g.replay()
+        torch.cuda.synchronize()
+        n = int(sizes[0])
+        assert bytes(out[0, :n].cpu().numpy().tobytes()) == oracle_c.encode_jpeg(f.numpy(), "420", 75, 0)
