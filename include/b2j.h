@@ -219,6 +219,8 @@ int b2j_bitpack(const int16_t *coefs, const uint32_t *offsets, const int64_t *to
  * decoupled look-back, and the bits are packed at their final offsets; 0xFF stuffing, JFIF
  * header and EOI follow.  Same outputs as b2j_block_bits + b2j_scan + b2j_bitpack.
  * workspace: b2j_entropy_workspace_bytes() bytes, 256-byte aligned. */
+/* Coefficients must be baseline-codable (what K1 produces): |AC| <= 1023 and DC differences within
+ * +-2047.  Anything else yields an undefined stream or sizes[] = INT64_MIN, never out-of-bounds writes. */
 size_t b2j_entropy_workspace_bytes(const b2j_image_desc *desc, int64_t out_cap);
 size_t b2j_entropy_workspace_bytes_opts(const b2j_image_desc *desc, int64_t out_cap, int opts);
 int b2j_entropy_encode(const int16_t *coefs, const b2j_image_desc *desc,

@@ -75,7 +75,7 @@ struct PrivSink {
     __device__ __forceinline__ void store(uint32_t w)
     {
         if (k < kCap) col[k * kCols] = w;
-        else ovf[(k - kCap) * kCols] = w;
+        else if (k < kPrivWords) ovf[(k - kCap) * kCols] = w;        // (coefficients outside the JPEG range: drop, never write past the column)
     }
     __device__ __forceinline__ uint32_t load(int i) const { return i < kCap ? col[i * kCols] : ovf[(i - kCap) * kCols]; }
     __device__ __forceinline__ void put(uint32_t val, int len)      // 1 <= len <= 32, val < 2^len
@@ -237,6 +237,10 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
         encode_block<EAGER, false>(s_mask[tid * 2], s_mask[tid * 2 + 1], diff, blk, s_dc + 16 * chroma, s_ac + 256 * chroma, sink);
         sink.flush();
         mybits = sink.bits();
+        if (mybits > (kPrivWords - 1) * 32) {                       // only with coefficients no baseline table can code
+            atomicExch(P.error_flag, 1);                            // -> every sizes[] becomes INT64_MIN
+            mybits = (kPrivWords - 1) * 32;
+        }
         s_nbits[tid] = (uint32_t)mybits;
     }
     // the lookahead blocks only have to supply the bits that complete this chunk's last word

@@ -362,3 +362,33 @@ def test_encode_is_cuda_graph_capturable(lj, oracle_c):
         torch.cuda.synchronize()
         n = int(sizes[0])
         assert bytes(out[0, :n].cpu().numpy().tobytes()) == oracle_c.encode_jpeg(f.numpy(), "420", 75, 0)
+
+
+def test_out_of_range_coefficients_stay_memory_safe(lj):
+    """b2j_entropy_encode is a public entry point: coefficients no baseline table can code (|v| up to
+    32767, outside the contract stated in include/b2j.h) give an undefined stream or an error verdict,
+    but never writes past the per-block scratch columns, and the workspace stays usable for the next,
+    valid call."""
+    L = lj.lib()
+    desc = lj.make_desc(64, 96, "444", 2)
+    g = lj.geometry(desc)
+    cap = 64 * 96 * 8
+    gen = torch.Generator().manual_seed(5)
+    bad = torch.randint(-32768, 32768, (2, g.blocks_per_frame, 64), generator=gen, dtype=torch.int32).to(torch.int16).cuda()
+    ws = torch.empty((L.b2j_entropy_workspace_bytes(ctypes.byref(desc), cap) + 256,), dtype=torch.uint8, device="cuda")
+    guard = torch.full((1 << 20,), 0x5A, dtype=torch.uint8, device="cuda")           # canary right behind the workspace arena
+    wp = (ws.data_ptr() + 255) & ~255
+    out = torch.zeros((2, cap), dtype=torch.uint8, device="cuda")
+    sizes = torch.zeros((2,), dtype=torch.int64, device="cuda")
+    qy, qc = lj.quant_tables(75)
+    ta, tb = lj._lib.table_arg(qy), lj._lib.table_arg(qc)
+    for zrl in (0, 1):
+        lj._lib.check(L.b2j_entropy_encode(bad.data_ptr(), ctypes.byref(desc), ta, tb, zrl, wp, out.data_ptr(), cap, sizes.data_ptr(), None))
+        torch.cuda.synchronize()
+        assert bool(((sizes < 0) | (sizes <= cap)).all())
+    assert bool((guard == 0x5A).all())
+    enc = lj.JpegEncoder("444", quality=75, out_cap=cap)
+    good = enc.coefficients(synth(lj).frame(64, 96, 23, 0).cuda()[None].repeat(2, 1, 1, 1))
+    lj._lib.check(L.b2j_entropy_encode(good.data_ptr(), ctypes.byref(desc), ta, tb, 0, wp, out.data_ptr(), cap, sizes.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert (sizes > 0).all() and int(sizes[0]) == int(sizes[1])
