@@ -82,7 +82,7 @@ class OracleC:
     def encode_jpeg(self, rgb, sub, quality, zrl):
         rgb = np.ascontiguousarray(rgb)
         h, w = rgb.shape[:2]
-        cap = h * w * 6 + 4096
+        cap = ((h + 15) // 16 * 16) * ((w + 15) // 16 * 16) * 6 + 4096      # padded to whole MCUs
         out = np.zeros(cap, np.uint8)
         n = self.lib.b2jo_encode_jpeg(self._p(rgb), h, w, int(sub), int(quality), int(zrl), self._p(out), ctypes.c_int64(cap))
         assert 0 < n <= cap

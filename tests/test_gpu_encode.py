@@ -392,3 +392,18 @@ def test_out_of_range_coefficients_stay_memory_safe(lj):
     lj._lib.check(L.b2j_entropy_encode(good.data_ptr(), ctypes.byref(desc), ta, tb, 0, wp, out.data_ptr(), cap, sizes.data_ptr(), None))
     torch.cuda.synchronize()
     assert (sizes > 0).all() and int(sizes[0]) == int(sizes[1])
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (1, 65535), (65535, 1), (3, 2)])
+def test_extreme_dimensions_bytes_equal_oracle(lj, oracle_c, shape):
+    """Smallest and largest baseline-JPEG dimensions (SOF0 holds 16-bit sizes): one pixel, one row of
+    65535 pixels, one column of 65535 pixels; everything else is edge replication."""
+    h, w = shape
+    g = torch.Generator().manual_seed(h * 7 + w)
+    frame = torch.randint(0, 256, (h, w, 3), generator=g, dtype=torch.uint8)
+    for sub in SUBS:
+        enc = lj.JpegEncoder(sub, quality=90, zrl="standard", out_cap=max(h, w) * 16 * 16 * 3 + 4096)
+        jpg = enc.encode(frame.cuda()[None])[0]
+        assert jpg == oracle_c.encode_jpeg(frame.numpy(), sub, 90, 1), (shape, sub)
+    with pytest.raises(lj.B2JError):
+        lj.geometry(lj.make_desc(65536, 8, "444", 1))
