@@ -135,6 +135,21 @@ int b2j_ycbcr2rgb(const uint8_t *y, const uint8_t *cb, const uint8_t *cr,
 int b2j_ycbcr422to444(const uint8_t *y, const uint8_t *cb_cr,
                       uint8_t *y_out, uint8_t *cb_out, uint8_t *cr_out, int64_t n_pixels, void *stream);
 
+/* [ext] ingest: converts other pixel layouts on the device into the packed,
+ * interleaved 8-bit RGB the encode path reads.  replaces: the host-side unpacking of the
+ * reference (test/model/enc_frame.py:7-10 `arr[..., 0..2]`; test/common.py:47-51
+ * `zip(*img.getdata())`).  Strides in bytes, 0 = packed; src_plane_stride only for
+ * B2J_LAYOUT_PLANAR_RGB (R plane, G plane, B plane); rgb: n_frames x height x width x 3. */
+#define B2J_LAYOUT_RGB 0
+#define B2J_LAYOUT_BGR 1
+#define B2J_LAYOUT_RGBA 2       /* alpha ignored, as enc_frame.py:8-10 does for RGBA PNGs */
+#define B2J_LAYOUT_BGRA 3
+#define B2J_LAYOUT_PLANAR_RGB 4
+#define B2J_LAYOUT_GRAY 5       /* r = g = b = sample */
+int b2j_ingest(const uint8_t *src, int layout, int32_t width, int32_t height, int32_t n_frames,
+               int64_t src_row_stride, int64_t src_plane_stride, int64_t src_frame_stride,
+               uint8_t *rgb, void *stream);
+
 /* [ext] plane subsampling with the same pair mean, horizontally (422) and then
  * vertically (420).  in: height x width, out: (height/v) x (width/2). */
 int b2j_chroma_subsample(const uint8_t *in, uint8_t *out, int32_t height, int32_t width,

@@ -56,6 +56,7 @@ SIGNATURES = {
     "b2j_rle_main": (c_int, [_P, _P, c_int64, c_int32, _P]),
     "b2j_rle_code": (c_int, [_P, _P, _P, c_int64, _P]),
     "b2j_dct_fixed": (c_int, [_P, _P, c_int64, _P]),
+    "b2j_ingest": (c_int, [_P, c_int, c_int32, c_int32, c_int32, c_int64, c_int64, c_int64, _P, _P]),
     "b2j_fused_block": (c_int, [_P, _DESC, _P, _P, _P, c_int, _P]),
     "b2j_block_bits": (c_int, [_P, _DESC, c_int, _P, _P]),
     "b2j_scan_workspace_bytes": (c_size_t, [_DESC]),
@@ -80,6 +81,7 @@ SUB = {"444": 444, "422": 422, "420": 420}
 ZRL = {"eager": 0, "standard": 1}
 CSC = {"jfif": 0, "xapp930": 1}
 QMODE = {"round": 0, "trunc": 1, "reciprocal": 2}
+LAYOUT = {"rgb": 0, "bgr": 1, "rgba": 2, "bgra": 3, "planar": 4, "gray": 5}
 DCT_MODE = {"model": 0, "fixed": 0x100}      # B2J_FUSED_DCT_FIXED / B2J_OPT_DCT_FIXED
 
 

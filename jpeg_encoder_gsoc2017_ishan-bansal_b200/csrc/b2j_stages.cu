@@ -76,6 +76,62 @@ __global__ void k_ycbcr422to444(const uint8_t *__restrict__ y, const uint8_t *__
     }
 }
 
+// ---- [ext] ingest: other pixel layouts -> the packed interleaved RGB the path reads.
+// The reference does this on the host with PIL (enc_frame.py:7-10 takes arr[..., 0..2]; test/common.py:47-51
+// unzips img.getdata()).  One thread per 4 output pixels (three 32-bit stores).
+struct IngestParams {
+    const uint8_t *src;
+    uint8_t *dst;
+    int width, height, layout;
+    long long src_row_stride, src_plane_stride, src_frame_stride, n_frames;
+};
+
+__device__ __forceinline__ void ingest_px(const IngestParams &P, const uint8_t *frame, int y, int x, uint32_t &r, uint32_t &g, uint32_t &b)
+{
+    const uint8_t *row = frame + (long long)y * P.src_row_stride;
+    switch (P.layout) {
+    case B2J_LAYOUT_RGB:  r = row[3 * x]; g = row[3 * x + 1]; b = row[3 * x + 2]; break;
+    case B2J_LAYOUT_BGR:  b = row[3 * x]; g = row[3 * x + 1]; r = row[3 * x + 2]; break;
+    case B2J_LAYOUT_RGBA: { const uchar4 q = reinterpret_cast<const uchar4 *>(row)[x]; r = q.x; g = q.y; b = q.z; } break;
+    case B2J_LAYOUT_BGRA: { const uchar4 q = reinterpret_cast<const uchar4 *>(row)[x]; b = q.x; g = q.y; r = q.z; } break;
+    case B2J_LAYOUT_PLANAR_RGB:
+        r = row[x]; g = row[P.src_plane_stride + x]; b = row[2 * P.src_plane_stride + x]; break;
+    default: r = g = b = row[x]; break;                       // B2J_LAYOUT_GRAY
+    }
+}
+
+__global__ void k_ingest(const __grid_constant__ IngestParams P)
+{
+    const long long groups_per_row = (P.width + 3) / 4;
+    const long long n = P.n_frames * P.height * groups_per_row;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int gx = (int)(i % groups_per_row);
+        const long long t = i / groups_per_row;
+        const int y = (int)(t % P.height);
+        const long long f = t / P.height;
+        const uint8_t *frame = P.src + f * P.src_frame_stride;
+        uint8_t *out = P.dst + ((f * P.height + y) * (long long)P.width + 4 * gx) * 3;
+        const int npx = min(4, P.width - 4 * gx);
+        uint32_t c[12];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t r = 0, g = 0, b = 0;
+            if (k < npx) ingest_px(P, frame, y, 4 * gx + k, r, g, b);
+            c[3 * k] = r; c[3 * k + 1] = g; c[3 * k + 2] = b;
+        }
+        if (npx == 4 && ((uintptr_t)out & 3) == 0) {
+            uint32_t *o = reinterpret_cast<uint32_t *>(out);
+            o[0] = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
+            o[1] = c[4] | (c[5] << 8) | (c[6] << 16) | (c[7] << 24);
+            o[2] = c[8] | (c[9] << 8) | (c[10] << 16) | (c[11] << 24);
+        } else {
+            for (int k = 0; k < 3 * npx; k++) out[k] = (uint8_t)c[k];
+        }
+    }
+}
+
 // ---- [ext] plane subsampling: pair mean horizontally, then (4:2:0) vertically
 __global__ void k_chroma_subsample(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
                                    int height, int width, int v2)
@@ -283,6 +339,32 @@ extern "C" int b2j_chroma_subsample(const uint8_t *in, uint8_t *out, int32_t hei
     long long n = (long long)(width / 2) * (v2 ? height / 2 : height);
     k_chroma_subsample<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(in, out, height, width, v2);
     B2J_LAUNCH_CHECK("k_chroma_subsample");
+    return B2J_OK;
+}
+
+extern "C" int b2j_ingest(const uint8_t *src, int layout, int32_t width, int32_t height, int32_t n_frames,
+                          int64_t src_row_stride, int64_t src_plane_stride, int64_t src_frame_stride, uint8_t *rgb,
+                          void *stream)
+{
+    B2J_REQUIRE(src && rgb, B2J_E_ARG, "b2j_ingest: null pointer");
+    B2J_REQUIRE(layout >= B2J_LAYOUT_RGB && layout <= B2J_LAYOUT_GRAY, B2J_E_ARG, "b2j_ingest: bad layout %d", layout);
+    B2J_REQUIRE(width >= 1 && height >= 1 && n_frames >= 1 && width <= 65535 && height <= 65535, B2J_E_SHAPE,
+                "b2j_ingest: bad shape %d x %d x %d", n_frames, height, width);
+    const int bpp = layout <= B2J_LAYOUT_BGR ? 3 : (layout <= B2J_LAYOUT_BGRA ? 4 : 1);
+    if (src_row_stride == 0) src_row_stride = (int64_t)width * bpp;
+    if (src_plane_stride == 0) src_plane_stride = src_row_stride * height;
+    if (src_frame_stride == 0) src_frame_stride = layout == B2J_LAYOUT_PLANAR_RGB ? 3 * src_plane_stride : src_row_stride * height;
+    B2J_REQUIRE(src_row_stride >= (int64_t)width * bpp, B2J_E_SHAPE, "b2j_ingest: row stride smaller than a row");
+    if (layout == B2J_LAYOUT_RGBA || layout == B2J_LAYOUT_BGRA)
+        B2J_REQUIRE(((uintptr_t)src & 3) == 0 && (src_row_stride & 3) == 0 && (src_frame_stride & 3) == 0, B2J_E_ALIGN,
+                    "b2j_ingest: 4-byte pixels need 4-byte aligned rows");
+    IngestParams P;
+    P.src = src; P.dst = rgb; P.width = width; P.height = height; P.layout = layout;
+    P.src_row_stride = src_row_stride; P.src_plane_stride = src_plane_stride; P.src_frame_stride = src_frame_stride;
+    P.n_frames = n_frames;
+    const long long n = (long long)n_frames * height * ((width + 3) / 4);
+    k_ingest<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(P);
+    B2J_LAUNCH_CHECK("k_ingest");
     return B2J_OK;
 }
 

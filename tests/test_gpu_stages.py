@@ -225,3 +225,36 @@ def test_dct_fixed_mode_operator(lj, oracle_c, golden):
     assert lj.to_signed(pk, 12) == G.dct_fixed(blocks[0]).tolist()
     with pytest.raises(ValueError):
         lj.DCT(mode="gateware")
+
+
+def test_ingest_layouts_on_device(lj, tmp_path):
+    """[ext] b2j_ingest / lj.to_rgb: BGR, RGBA, BGRA, planar and grey buffers (with row, plane and frame
+    strides) become the packed RGB the path reads; read_image() follows the model's file reading
+    (enc_frame.py:7-10: channels 0..2 of the decoded array)."""
+    from PIL import Image
+    g = torch.Generator().manual_seed(9)
+    for (n, h, w) in ((1, 5, 7), (3, 16, 33), (2, 31, 64)):
+        rgb = torch.randint(0, 256, (n, h, w, 3), generator=g, dtype=torch.uint8)
+        a = torch.randint(0, 256, (n, h, w, 1), generator=g, dtype=torch.uint8)
+        dev = rgb.cuda()
+        assert torch.equal(lj.to_rgb(dev, "rgb"), dev)
+        assert torch.equal(lj.to_rgb(dev.flip(-1).contiguous(), "bgr"), dev)
+        assert torch.equal(lj.to_rgb(torch.cat([rgb, a], -1).cuda(), "rgba"), dev)
+        assert torch.equal(lj.to_rgb(torch.cat([rgb.flip(-1), a], -1).cuda(), "bgra"), dev)
+        assert torch.equal(lj.to_rgb(dev.permute(0, 3, 1, 2).contiguous(), "planar"), dev)
+        grey = dev[..., 0].contiguous()
+        assert torch.equal(lj.to_rgb(grey, "gray"), grey[..., None].expand(-1, -1, -1, 3))
+        # strided views: a crop of a wider / taller buffer, every second frame
+        big = torch.randint(0, 256, (2 * n, h + 3, w + 5, 3), generator=g, dtype=torch.uint8).cuda()
+        view = big[::2, 1:h + 1, 2:w + 2]
+        assert torch.equal(lj.to_rgb(view, "bgr"), view.flip(-1).contiguous())
+        pl = torch.randint(0, 256, (n, 3, h + 2, w + 4), generator=g, dtype=torch.uint8).cuda()[:, :, 1:h + 1, 3:w + 3]
+        assert torch.equal(lj.to_rgb(pl, "planar"), pl.permute(0, 2, 3, 1).contiguous())
+        assert torch.equal(lj.to_rgb(dev[0], "rgb"), dev[0])
+    arr = torch.randint(0, 256, (24, 40, 4), generator=g, dtype=torch.uint8).numpy()
+    Image.fromarray(arr, "RGBA").save(str(tmp_path / "a.png"))
+    Image.fromarray(arr[..., 0], "L").save(str(tmp_path / "l.png"))
+    assert torch.equal(lj.read_image(str(tmp_path / "a.png")).cpu(), torch.from_numpy(arr[..., :3].copy()))
+    assert torch.equal(lj.read_image(str(tmp_path / "l.png")).cpu(), torch.from_numpy(arr[..., :1].repeat(3, axis=2)))
+    with pytest.raises(ValueError):
+        lj.to_rgb(torch.zeros((4, 4, 3), dtype=torch.uint8).cuda(), "yuv")
