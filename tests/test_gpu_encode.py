@@ -407,3 +407,28 @@ def test_extreme_dimensions_bytes_equal_oracle(lj, oracle_c, shape):
         assert jpg == oracle_c.encode_jpeg(frame.numpy(), sub, 90, 1), (shape, sub)
     with pytest.raises(lj.B2JError):
         lj.geometry(lj.make_desc(65536, 8, "444", 1))
+
+
+def test_random_parameter_space_bytes_equal_oracle(lj, oracle_c):
+    """Seeded sweep over shape x subsampling x quality x ZRL policy x restart interval x DCT mode x
+    content: every file byte-identical to the oracle's (batches of 1-3 frames)."""
+    rng = np.random.default_rng(20171020)
+    s = synth(lj)
+    for case in range(48):
+        h, w = int(rng.integers(1, 300)), int(rng.integers(1, 1300))
+        sub = SUBS[case % 3]
+        q = int(rng.integers(1, 101))
+        zi = int(rng.integers(0, 2))
+        ri = int(rng.choice([0, 0, 0, 1, 3, 11, 64, 500]))
+        fixed = bool(case % 5 == 4)
+        n = 1 + case % 3
+        kind = ("photo", "noise", "grey", "photo")[case % 4]
+        frames = torch.stack([s.frame(h, w, 31 + case, i, kind) for i in range(n)])
+        if kind == "grey":
+            frames[..., :] = int(rng.integers(0, 256))
+        enc = lj.JpegEncoder(sub, quality=q, zrl=("eager", "standard")[zi], restart_interval=ri,
+                             dct="fixed" if fixed else "model", out_cap=((h + 15) // 16 * 16) * ((w + 15) // 16 * 16) * 6 + 4096)
+        files = enc.encode(frames.cuda())
+        for i in range(n):
+            want = oracle_c.encode_jpeg(frames[i].numpy(), sub, q, zi | (0x100 if fixed else 0) | (ri << 16))
+            assert files[i] == want, (case, h, w, sub, q, zi, ri, fixed, kind, i)

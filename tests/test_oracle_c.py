@@ -124,3 +124,29 @@ def test_restart_intervals_c_equals_numpy_and_libjpeg_decodes_them(oracle_c):
                 assert rc == 0 and np.array_equal(co, ref_coefs)
                 if zrl == "standard":
                     assert np.array_equal(np.asarray(Image.open(io.BytesIO(a)).convert("RGB")), ref_px)
+
+
+def test_random_parameter_space_c_equals_numpy(oracle_c):
+    """Seeded sweep over shape x subsampling x quality x ZRL policy x restart interval: the two
+    restatements of the [ext] parts agree byte for byte and the decoder recovers the coefficients."""
+    from oracle import jpeg_ext as J
+    rng = np.random.default_rng(20171019)
+    for case in range(24):
+        h, w = int(rng.integers(1, 70)), int(rng.integers(1, 90))
+        sub = ("444", "422", "420")[case % 3]
+        q = int(rng.integers(1, 101))
+        zi = int(rng.integers(0, 2))
+        ri = int(rng.choice([0, 0, 1, 2, 5, 17]))
+        kind = case % 4
+        if kind == 0:
+            img = rng.integers(0, 256, (h, w, 3)).astype(np.uint8)
+        elif kind == 1:
+            img = np.full((h, w, 3), int(rng.integers(0, 256)), np.uint8)
+        else:
+            base = np.add.outer(np.arange(h) * int(rng.integers(0, 6)), np.arange(w) * int(rng.integers(0, 6)))[..., None]
+            img = np.clip(base + rng.integers(-9, 10, (h, w, 3)) + rng.integers(0, 200, 3), 0, 255).astype(np.uint8)
+        a = J.encode_jpeg(img, sub, q, ("eager", "standard")[zi], ri)
+        assert a == oracle_c.encode_jpeg(img, sub, q, zi | (ri << 16)), (case, h, w, sub, q, zi, ri)
+        rc, co = oracle_c.decode_coefficients(a, h, w, sub)
+        qy, qc = oracle_c.quant_tables(q)
+        assert rc == 0 and np.array_equal(co, oracle_c.coefficients(img, sub, qy, qc)), case
