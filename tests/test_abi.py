@@ -114,3 +114,22 @@ def test_no_cuda_means_a_loud_error(lj):
         lj.JpegEncoder("420", 75).encode(torch.zeros((16, 16, 3), dtype=torch.uint8))
     with pytest.raises(RuntimeError):
         lj.DCT().process([0] * 64)
+
+
+def test_header_is_valid_c99_and_host_entry_points_work(tmp_path):
+    """include/b2j.h compiles as strict C99 (the language a cgo / JNI / N-API stub is written in) and a
+    plain C client linked against libb2j.so can use every host-only entry point without a GPU."""
+    import os
+    import subprocess
+    import litejpeg_b200 as lj
+    lj.lib()                                            # builds the library if needed
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "jpeg_encoder_gsoc2017_ishan-bansal_b200")
+    exe = str(tmp_path / "abi_host_only")
+    cmd = ["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"),
+           os.path.join(root, "tests", "c", "abi_host_only.c"), "-o", exe, "-L", libdir, "-l:libb2j.so", "-Wl,-rpath," + libdir]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([exe], capture_output=True, text=True)
+    assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
+    assert "120x68" in run.stdout
