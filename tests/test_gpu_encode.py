@@ -432,3 +432,28 @@ def test_random_parameter_space_bytes_equal_oracle(lj, oracle_c):
         for i in range(n):
             want = oracle_c.encode_jpeg(frames[i].numpy(), sub, q, zi | (0x100 if fixed else 0) | (ri << 16))
             assert files[i] == want, (case, h, w, sub, q, zi, ri, fixed, kind, i)
+
+
+def test_pure_c_client_of_the_host_buffer_encoder(lj, oracle_c, tmp_path):
+    """tests/c/encode_raw.c: a C99 program that only knows include/b2j.h and libb2j.so (no Python, no
+    torch in the process) encodes raw RGB frames from a file; the files equal the oracle's."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "jpeg_encoder_gsoc2017_ishan-bansal_b200")
+    exe = str(tmp_path / "encode_raw")
+    res = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-D_POSIX_C_SOURCE=200809L", "-I",
+                          os.path.join(root, "include"), os.path.join(root, "tests", "c", "encode_raw.c"), "-o", exe, "-L", libdir,
+                          "-l:libb2j.so", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    s = synth(lj)
+    frames = torch.stack([s.frame(270, 484, 41, i) for i in range(6)])
+    raw = str(tmp_path / "in.rgb")
+    frames.numpy().tofile(raw)
+    for sub, q, zrl, ri in (("420", 75, 0, 0), ("444", 92, 1, 0), ("422", 60, 1, 31)):
+        prefix = str(tmp_path / ("out_%s_" % sub))
+        run = subprocess.run([exe, raw, "484", "270", "6", sub, str(q), str(zrl), str(ri), prefix], capture_output=True, text=True)
+        assert run.returncode == 0, (run.stdout, run.stderr)
+        for i in range(6):
+            got = open("%s%d.jpg" % (prefix, i), "rb").read()
+            assert got == oracle_c.encode_jpeg(frames[i].numpy(), sub, q, zrl | (ri << 16)), (sub, i)
