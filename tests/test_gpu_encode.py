@@ -457,3 +457,40 @@ def test_pure_c_client_of_the_host_buffer_encoder(lj, oracle_c, tmp_path):
         for i in range(6):
             got = open("%s%d.jpg" % (prefix, i), "rb").read()
             assert got == oracle_c.encode_jpeg(frames[i].numpy(), sub, q, zrl | (ri << 16)), (sub, i)
+
+
+def test_concurrent_callers_on_separate_streams(lj, oracle_c):
+    """The ABI contract says re-entrant, no global state, one stream per caller thread: four threads
+    encode different batches concurrently, each on its own stream and workspace, five times over."""
+    import threading
+    s = synth(lj)
+    jobs = [("420", 75, "eager", 0), ("444", 90, "standard", 0), ("422", 50, "eager", 9), ("420", 30, "standard", 0)]
+    batches = [torch.stack([s.frame(200 + 8 * t, 328 - 16 * t, 51 + t, i) for i in range(3)]) for t in range(4)]
+    want = [[oracle_c.encode_jpeg(batches[t][i].numpy(), jobs[t][0], jobs[t][1], (0 if jobs[t][2] == "eager" else 1) | (jobs[t][3] << 16))
+             for i in range(3)] for t in range(4)]
+    errors = []
+
+    def worker(t):
+        try:
+            sub, q, zrl, ri = jobs[t]
+            torch.cuda.set_device(0)
+            stream = torch.cuda.Stream()
+            enc = lj.JpegEncoder(sub, quality=q, zrl=zrl, restart_interval=ri, out_cap=300 * 400 * 6)
+            dev = batches[t].cuda()
+            for _ in range(5):
+                with torch.cuda.stream(stream):
+                    out, sizes = enc.encode_device(dev, stream=stream)
+                stream.synchronize()
+                host, sz = out.cpu(), sizes.cpu()
+                for i in range(3):
+                    if bytes(host[i, :int(sz[i])].numpy().tobytes()) != want[t][i]:
+                        errors.append((t, i))
+        except Exception as e:          # surfaced below
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
