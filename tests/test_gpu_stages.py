@@ -258,3 +258,28 @@ def test_ingest_layouts_on_device(lj, tmp_path):
     assert torch.equal(lj.read_image(str(tmp_path / "l.png")).cpu(), torch.from_numpy(arr[..., :1].repeat(3, axis=2)))
     with pytest.raises(ValueError):
         lj.to_rgb(torch.zeros((4, 4, 3), dtype=torch.uint8).cuda(), "yuv")
+
+
+def test_integration_md_ctypes_stub_runs_as_written(lj, oracle_c, golden):
+    """INTEGRATION.md section 2 is a ctypes stub a reference maintainer would drop under test/: the code
+    blocks are executed verbatim (only the library path is resolved) and checked against the oracle."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    sec = text[text.index("## 2. Bind the C ABI directly"):text.index("## 3. From C")]
+    code = "\n".join(re.findall(r"```python\n(.*?)```", sec, flags=re.S))
+    code = code.replace('ctypes.CDLL("libb2j.so")', 'ctypes.CDLL(%r)' % lj._lib.LIB_PATH)
+    cudart = [p for p in os.popen("ldd %s" % lj._lib.LIB_PATH).read().split() if "libcudart" in p and "/" in p]
+    if cudart:
+        code = code.replace('ctypes.CDLL("libcudart.so")', 'ctypes.CDLL(%r)' % cudart[0])
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    blk = golden.stages["dct_in"][3].tolist()
+    out = ns["dct_packet"](blk)
+    assert lj.to_signed(out, 12) == golden.stages["dct_out"][3].tolist()
+    zz = ns["zigzag_packet"](list(range(64)))
+    assert zz == M.zigzag(np.arange(64)).tolist()
+    rgb = golden.lena["rgb"][None, :64, :96].copy()
+    files = ns["encode_frames"](rgb, 444, 85, 0)
+    assert files[0] == oracle_c.encode_jpeg(rgb[0], "444", 85, 0)
