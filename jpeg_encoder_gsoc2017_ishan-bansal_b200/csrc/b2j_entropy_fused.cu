@@ -1,6 +1,7 @@
 // Fused single-pass entropy coder (K2 + K3 + K4 packing in one kernel).
 //
-// One CTA per chunk of 128 consecutive blocks of a frame, in launch order (ticket):
+// Persistent CTAs take chunks of 128 consecutive blocks of a stream by ticket (a stream is a frame,
+// or with [ext] restart intervals one segment of a frame; tickets interleave the streams):
 //   1. the chunk's coefficients (+ 8 lookahead blocks) are loaded once, coalesced, into
 //      shared memory (33-word pitch per block: conflict free both for the cooperative
 //      stores and for the per-thread reads); the loading thread also records which of its
@@ -15,8 +16,10 @@
 //      its block: its own private bits shifted to the final alignment, completed with the
 //      first bits of the following blocks (the 8 lookahead blocks cover the chunk's tail).
 //      Every output word has exactly one writer: plain stores, no atomics, no zero-init;
-//   5. the last block of a frame pads the final byte with 1s; total_bits[frame] is written.
-// 0xFF stuffing and JFIF framing then run on the packed stream (launch_stuffing).
+//   5. whichever thread composes the stream's final word pads its last byte with 1s (that thread can
+//      sit in the previous chunk when the tail is a run of 4-6 bit blocks); total_bits[stream] is
+//      written; 0xFF bytes are counted per 4096-byte chunk of the packed stream on the fly.
+// 0xFF stuffing, RSTm / EOI markers and JFIF framing then run on the packed stream (launch_stuffing).
 #include "b2j_entropy.cuh"
 #include <cstdlib>
 

@@ -5,6 +5,7 @@
 // Output layout: coefs[frame][mcu][block_in_mcu][64] int16, zig-zag order, MCUs
 // row-major, blocks of an MCU in scan order (luma raster, then Cb, then Cr).
 //
+// FIXED selects the [ext] gateware fixed-point DCT instead of the float64 model (b2j_block.cuh).
 // Two variants:
 //   simple - one thread per 8x8 block straight from global memory; any geometry;
 //            kept as the cross-check and the un-tiled fallback.
@@ -13,8 +14,9 @@
 //                    copies (cp.async.bulk, one per row, completion on an
 //                    mbarrier) when rows are 16-byte aligned, else by a
 //                    cooperative copy;
-//            (A)     every thread converts 8-pixel patches to Y/Cb/Cr with the
-//                    integer restatement of the model's colour formulas and
+//            (A)     every thread converts items of 4 pixels x V rows to Y/Cb/Cr with the
+//                    integer restatement of the model's colour formulas (the inputs
+//                    where the float64 model differs are patched from tables) and
 //                    writes 8-bit planes (chroma already subsampled) to smem;
 //            (B)     every thread takes whole 8x8 blocks from the planes, runs
 //                    the model's DCT graph in registers (FP64 pipe), quantises
