@@ -494,3 +494,38 @@ def test_concurrent_callers_on_separate_streams(lj, oracle_c):
     for th in threads:
         th.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("kind", ["noise", "photo", "grey"])
+def test_no_byte_is_written_outside_the_stated_ranges(lj, kind):
+    """Own bounds check (no sanitizer on this pool): guard bytes behind the workspace the library asked
+    for, behind every output slot's used bytes, behind the last slot and behind `sizes` stay intact,
+    for worst-case (noise) and best-case (grey) content, with and without restart intervals."""
+    L = lj.lib()
+    s = synth(lj)
+    n, h, w = 3, 136, 1048
+    frames = torch.stack([s.frame(h, w, 61, i, kind) for i in range(n)]).cuda()
+    desc = lj.make_desc(h, w, "420", n)
+    cap = 136 * 1048 * 3 + 4096
+    qy, qc = lj.quant_tables(95)
+    ta, tb = lj._lib.table_arg(qy), lj._lib.table_arg(qc)
+    G = 1 << 16
+    for opts in (0, 1, lj._lib.opt_restart(7), 1 | lj._lib.opt_restart(66) | 0x100):
+        need = int(L.b2j_encode_workspace_bytes_opts(ctypes.byref(desc), cap, opts))
+        ws = torch.full((need + 256 + G,), 0xA5, dtype=torch.uint8, device="cuda")
+        wp = (ws.data_ptr() + 255) & ~255
+        pad = wp - ws.data_ptr()
+        out = torch.full((n * cap + G,), 0xC3, dtype=torch.uint8, device="cuda")
+        sizes = torch.full((n + 8,), -12345, dtype=torch.int64, device="cuda")
+        lj._lib.check(L.b2j_encode(frames.data_ptr(), ctypes.byref(desc), 0, ta, tb, opts, wp, need, out.data_ptr(), cap,
+                                   sizes.data_ptr(), None))
+        torch.cuda.synchronize()
+        assert bool((ws[pad + need:] == 0xA5).all()), "write behind the workspace"
+        assert bool((out[n * cap:] == 0xC3).all()), "write behind the last output slot"
+        assert bool((sizes[n:] == -12345).all()), "write behind sizes[]"
+        sz = sizes[:n].cpu()
+        assert int(sz.min()) > 0
+        for i in range(n):
+            assert bool((out[i * cap + int(sz[i]):(i + 1) * cap] == 0xC3).all()), "write behind the file inside slot %d" % i
+            assert bytes(out[i * cap:i * cap + 2].cpu().numpy().tobytes()) == b"\xFF\xD8"
+            assert bytes(out[i * cap + int(sz[i]) - 2:i * cap + int(sz[i])].cpu().numpy().tobytes()) == b"\xFF\xD9"
