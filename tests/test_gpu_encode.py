@@ -529,3 +529,21 @@ def test_no_byte_is_written_outside_the_stated_ranges(lj, kind):
             assert bool((out[i * cap + int(sz[i]):(i + 1) * cap] == 0xC3).all()), "write behind the file inside slot %d" % i
             assert bytes(out[i * cap:i * cap + 2].cpu().numpy().tobytes()) == b"\xFF\xD8"
             assert bytes(out[i * cap + int(sz[i]) - 2:i * cap + int(sz[i])].cpu().numpy().tobytes()) == b"\xFF\xD9"
+
+
+def test_example_script_encodes_a_png(lj, oracle_c, golden, tmp_path):
+    """examples/encode_image.py: PNG in, JPEG out, equal to the oracle's file and decodable by libjpeg."""
+    import os
+    import subprocess
+    import sys as _sys
+    from PIL import Image
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rgb = golden.lena["rgb"][:200, :312]
+    src, dst = str(tmp_path / "in.png"), str(tmp_path / "out.jpg")
+    Image.fromarray(rgb).save(src)
+    run = subprocess.run([_sys.executable, os.path.join(root, "examples", "encode_image.py"), src, dst, "--sub", "444",
+                          "--quality", "85", "--zrl", "eager"], capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr
+    got = open(dst, "rb").read()
+    assert got == oracle_c.encode_jpeg(rgb, "444", 85, 0)
+    assert Image.open(io.BytesIO(got)).size == (312, 200)
