@@ -26,7 +26,6 @@
 #include "b2j_common.cuh"
 #include "b2j_math.cuh"
 #include "b2j_block.cuh"
-#include <cstdlib>
 
 namespace b2j {
 
@@ -395,33 +394,98 @@ __global__ void __launch_bounds__(kThreads, B2J_K1_MIN_CTAS) k_fused_tiled(const
     }
 }
 
-template <int H, int V, bool FIXED>
-static int launch_fused(const FusedParams &P, const Geo &g, int variant, cudaStream_t st)
+}  // namespace b2j
+#include "b2j_fused_stream.cuh"     // =========================================================== stream variant
+namespace b2j {
+
+// Device attributes and occupancy are looked up once per device and kernel instantiation (the
+// single-frame path is launch-latency bound).
+struct LaunchInfo {
+    int sms = 0, per_sm = 0;
+};
+static const int kMaxDevices = 64;
+
+template <class Kernel>
+static int launch_info(Kernel kernel, int threads, int smem, LaunchInfo *cache, LaunchInfo *out)
 {
+    int dev = 0;
+    B2J_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) dev = kMaxDevices - 1;                  // (not cached correctly beyond 64 devices: recomputed)
+    LaunchInfo li = cache[dev];
+    if (li.sms == 0 || dev == kMaxDevices - 1) {
+        B2J_CUDA(cudaDeviceGetAttribute(&li.sms, cudaDevAttrMultiProcessorCount, dev));
+        B2J_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        B2J_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&li.per_sm, kernel, threads, smem));
+        if (li.per_sm < 1) li.per_sm = 1;
+        cache[dev] = li;                                                       // benign race: every writer stores the same values
+    }
+    *out = li;
+    return B2J_OK;
+}
+
+// The frames as a [frame][row][byte] tensor for the stream kernel's region loads.  Returns false when the
+// layout cannot be described (unaligned base or strides, driver without the entry point): the kernel then
+// copies every region byte-wise.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static bool make_frame_map(const FusedParams &P, int box_bytes, int box_rows, CUtensorMap *map)
+{
+    static EncodeTiledFn encode = [] {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            fn = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(fn);
+    }();
+    memset(map, 0, sizeof *map);
+    if (!encode || !P.aligned || P.row_stride >= (1LL << 40) || P.frame_stride >= (1LL << 40)) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)P.width * 3, (cuuint64_t)P.height, (cuuint64_t)P.n_frames};
+    const cuuint64_t strides[2] = {(cuuint64_t)P.row_stride, (cuuint64_t)P.frame_stride};
+    const cuuint32_t box[3] = {(cuuint32_t)box_bytes, (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t *>(P.rgb), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int H, int V, bool FIXED>
+static int launch_fused(const FusedParams &P0, const Geo &g, int variant, cudaStream_t st)
+{
+    FusedParams P = P0;
     if (variant == B2J_FUSED_SIMPLE) {
         const long long nblk = (long long)g.n_frames * g.blocks_per_frame;
         k_fused_simple<H, V, FIXED><<<(unsigned)((nblk + 127) / 128), 128, 0, st>>>(P);
         B2J_LAUNCH_CHECK("k_fused_simple");
         return B2J_OK;
     }
+    if (variant == B2J_FUSED_STREAM) {
+        using SS = StreamShape<H, V>;
+        const int regions_x = (g.mcus_x * 8 * H + SS::kRegW - 1) / SS::kRegW;
+        const long long n_regions = (long long)regions_x * g.mcus_y * g.n_frames;
+        if (n_regions < 0xFFF00000LL) {
+            static LaunchInfo cache[kMaxDevices];
+            LaunchInfo li;
+            int rc = launch_info(k_fused_stream<H, V, FIXED>, kStreamThreads, SS::kSmem, cache, &li);
+            if (rc) return rc;
+            const long long ctas_needed = (n_regions + kStreamWarps - 1) / kStreamWarps;
+            const long long grid = ctas_needed < (long long)li.per_sm * li.sms ? ctas_needed : (long long)li.per_sm * li.sms;
+            CUtensorMap map;
+            if (!make_frame_map(P, SS::kRawPitch, SS::kRows, &map)) P.aligned = 0;
+            k_fused_stream<H, V, FIXED><<<(unsigned)grid, kStreamThreads, SS::kSmem, st>>>(P, map, (unsigned)n_regions, regions_x);
+            B2J_LAUNCH_CHECK("k_fused_stream");
+            return B2J_OK;
+        }
+        // (more than 2^32 regions in one call: the tiled kernel has 64-bit tile indices)
+    }
     using TS = TileShape<H, V>;
     const int tiles_x = (g.mcus_x * 8 * H + kTileW - 1) / kTileW;
     const long long n_tiles = (long long)tiles_x * g.mcus_y * g.n_frames;
-    int dev = 0, sms = 148;
-    B2J_CUDA(cudaGetDevice(&dev));
-    B2J_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    B2J_CUDA(cudaFuncSetAttribute(k_fused_tiled<H, V, FIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS::kSmem));
-    int per_sm = 2;
-    B2J_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_tiled<H, V, FIXED>, kThreads, TS::kSmem));
-#ifdef B2J_K1_MAX_CTAS
-    if (per_sm > B2J_K1_MAX_CTAS) per_sm = B2J_K1_MAX_CTAS;
-#endif
-    if (const char *cap = getenv("B2J_K1_CTAS_PER_SM")) {               // tuning knob: leave room for a concurrent kernel
-        const int c = atoi(cap);
-        if (c >= 1 && c < per_sm) per_sm = c;
-    }
-    if (per_sm < 1) per_sm = 1;
-    const long long grid = n_tiles < (long long)per_sm * sms ? n_tiles : (long long)per_sm * sms;   // persistent CTAs
+    static LaunchInfo cache[kMaxDevices];
+    LaunchInfo li;
+    int rc = launch_info(k_fused_tiled<H, V, FIXED>, kThreads, TS::kSmem, cache, &li);
+    if (rc) return rc;
+    const long long grid = n_tiles < (long long)li.per_sm * li.sms ? n_tiles : (long long)li.per_sm * li.sms;   // persistent CTAs
     k_fused_tiled<H, V, FIXED><<<(unsigned)grid, kThreads, TS::kSmem, st>>>(P, n_tiles, tiles_x);
     B2J_LAUNCH_CHECK("k_fused_tiled");
     return B2J_OK;
@@ -437,7 +501,7 @@ extern "C" int b2j_fused_block(const uint8_t *rgb, const b2j_image_desc *desc, c
     B2J_REQUIRE(rgb && coefs && qy_host && qc_host, B2J_E_ARG, "b2j_fused_block: null pointer");
     const bool fixed = (variant & B2J_FUSED_DCT_FIXED) != 0;
     variant &= ~B2J_FUSED_DCT_FIXED;
-    B2J_REQUIRE(variant >= B2J_FUSED_AUTO && variant <= B2J_FUSED_TILED, B2J_E_ARG, "b2j_fused_block: bad variant %d", variant);
+    B2J_REQUIRE(variant >= B2J_FUSED_AUTO && variant <= B2J_FUSED_STREAM, B2J_E_ARG, "b2j_fused_block: bad variant %d", variant);
     B2J_REQUIRE(((uintptr_t)coefs & 15) == 0, B2J_E_ALIGN, "b2j_fused_block: coefs must be 16-byte aligned");
     Geo g;
     int rc = make_geo(desc, &g);
@@ -451,7 +515,10 @@ extern "C" int b2j_fused_block(const uint8_t *rgb, const b2j_image_desc *desc, c
     P.aligned = (((uintptr_t)rgb & 15) == 0 && (g.row_stride & 15) == 0 && (g.frame_stride & 15) == 0) ? 1 : 0;
     make_quant_mul(qy_host, qc_host, &P.qm);
     cudaStream_t st = as_stream(stream);
-    if (variant == B2J_FUSED_AUTO) variant = B2J_FUSED_TILED;
+#ifndef B2J_FUSED_DEFAULT
+#define B2J_FUSED_DEFAULT B2J_FUSED_STREAM
+#endif
+    if (variant == B2J_FUSED_AUTO) variant = B2J_FUSED_DEFAULT;
     if (fixed) {
         if (g.h == 1) return launch_fused<1, 1, true>(P, g, variant, st);
         if (g.v == 1) return launch_fused<2, 1, true>(P, g, variant, st);

@@ -1,0 +1,17 @@
+#!/bin/bash
+# build_variant.sh NAME "-DFLAG=.. -DFLAG2=.."  ->  jpeg_encoder_gsoc2017_ishan-bansal_b200/variants/libb2j_NAME.so
+# (a copy of the library with other compile-time knobs, for A/B timing on one GPU box; git-ignored)
+set -e
+NAME=$1; FLAGS=$2
+ROOT=$(cd "$(dirname "$0")/../.." && pwd)
+SRC=$ROOT/jpeg_encoder_gsoc2017_ishan-bansal_b200/csrc
+OUT=$ROOT/jpeg_encoder_gsoc2017_ishan-bansal_b200/variants
+TMP=$(mktemp -d)
+ARCH="-gencode arch=compute_100a,code=sm_100a"
+for f in b2j_common b2j_stages b2j_fused b2j_entropy b2j_entropy_fused b2j_encode; do
+  nvcc $ARCH -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC -Xptxas -v $FLAGS -c -o $TMP/$f.o $SRC/$f.cu 2> $TMP/$f.log &
+done
+wait
+nvcc $ARCH -shared -o $OUT/libb2j_$NAME.so $TMP/*.o -lcudart
+grep -A2 "k_fused_streamILi2ELi2ELb0" $TMP/b2j_fused.log | grep -E "registers|spill" | tr '\n' ' '; echo " -> libb2j_$NAME.so"
+rm -rf $TMP
