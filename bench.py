@@ -4,19 +4,21 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on host cores
 
-Workload (BASELINE.json configs[2], the configuration the Mpixel/s metric is quoted on): per GPU a
-batch of 256 synthetic 1920x1080 RGB frames, 4:2:0, quality 75 -> 256 JFIF files.  One "step" is one
-pass of the whole hot path (K1 fused block kernel; K2-K4 fused entropy kernel: block bits, scan with
-look-back, bit packing; 0xFF stuffing + JFIF framing)
-over that batch.  Frames are independent, so ranks shard by frames with no data-path collective
-(weak scaling: every rank encodes its own 256-frame batch).
+Workload (BASELINE.json configs[2], the configuration the Mpixel/s metric is quoted on): a batch of 256
+synthetic 1920x1080 RGB frames, 4:2:0, quality 75 -> 256 JFIF files, sharded across the N GPUs
+(rank g encodes frames [g*256/N, (g+1)*256/N): strong scaling, the named batch; `--scaling weak` gives
+every rank its own 256 frames instead).  One "step" is one pass of the whole hot path (K1 fused block
+kernel; K2-K4 fused entropy kernel: block bits, scan with look-back, bit packing; 0xFF stuffing + JFIF
+framing) over that batch.  Frames are independent: no data-path collective.
 
 value : whole-job Mpixel/s (source pixels) with the batch already resident in HBM, CUDA-event timed,
         max over ranks.  The 1.59 GB input is far larger than the 126 MB L2, so every step streams
         from HBM (config.l2 = "input > L2").
-e2e   : the same metric through the host-buffer entry point of the C ABI
-        (b2j_encoder_encode_host): pinned host RGB in, JFIF bytes in pinned host memory out, H2D and
-        D2H copies inside the timed region.
+e2e   : the same metric through the host-buffer entry point of the C ABI: ONE call of
+        b2j_multi_encoder_encode_host on rank 0 over the devices of all ranks (pinned host RGB of the
+        whole batch in, JFIF bytes in pinned host memory out, H2D and D2H copies inside the timed
+        region), with the box's concurrent host-to-device copy time for the same batch measured
+        beside it (e2e.frac_of_h2d_ceiling).
 roofline : K1 (the dominant kernel), algorithmic bytes 6 B per padded pixel (3 B RGB read + 1.5
         int16 coefficients written) / its mean duration measured with CUDA events inside the timed
         steps, against MEASURED_PEAKS.json hbm_gbs.
@@ -42,15 +44,15 @@ FRAMES_PER_GPU = 256
 UNIQUE_FRAMES = 32
 CONFIG_IDX = 2
 KIND = "photo"
-WORKLOAD = "batch of %d synthetic 1920x1080 RGB frames per GPU, 4:2:0, quality 75 (BASELINE configs[2])"
+WORKLOAD = "batch of %d synthetic 1920x1080 RGB frames, 4:2:0, quality 75 (BASELINE configs[2])"
 # The other BASELINE.json configs, for the per-config table in profiles/ (the driver's line is the default, configs[2]).
-# name: (height, width, subsampling, quality, frames per GPU, seed index, label)
+# name: (height, width, subsampling, quality, frames of the batch, seed index, label)
 PRESETS = {
     "1": (1080, 1920, "420", 75, 1, 1, "single synthetic 1920x1080 RGB frame, 4:2:0, quality 75 (BASELINE configs[1]); frames=%d"),
     "2": (1080, 1920, "420", 75, 256, 2, WORKLOAD),
-    "3a": (2160, 3840, "444", 90, 64, 3, "batch of %d synthetic 3840x2160 frames per GPU, 4:4:4, quality 90 (BASELINE configs[3])"),
-    "3b": (2160, 3840, "420", 90, 64, 3, "batch of %d synthetic 3840x2160 frames per GPU, 4:2:0, quality 90 (BASELINE configs[3])"),
-    "4": (4320, 7680, "420", 75, 16, 4, "batch of %d synthetic 7680x4320 frames per GPU, 4:2:0, quality 75 (BASELINE configs[4])"),
+    "3a": (2160, 3840, "444", 90, 64, 3, "batch of %d synthetic 3840x2160 frames, 4:4:4, quality 90 (BASELINE configs[3])"),
+    "3b": (2160, 3840, "420", 90, 64, 3, "batch of %d synthetic 3840x2160 frames, 4:2:0, quality 90 (BASELINE configs[3])"),
+    "4": (4320, 7680, "420", 75, 16, 4, "batch of %d synthetic 7680x4320 frames, 4:2:0, quality 75 (BASELINE configs[4])"),
 }
 METRIC = "Mpixel/s full JPEG encode (RGB -> JFIF bytes)"
 UNIT = "Mpixel/s"
@@ -63,7 +65,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=None, help="frames per GPU (default: the named workload)")
+    ap.add_argument("--frames", type=int, default=None, help="frames of the batch (default: the named workload)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default): the named batch is sharded across the GPUs; weak: every GPU gets the whole batch size")
     ap.add_argument("--config", default="2", choices=sorted(PRESETS), help="BASELINE.json config (default 2, the headline)")
     ap.add_argument("--dct", default="model", choices=["model", "fixed"],
                     help="model = float64 model arithmetic (parity path, the headline); fixed = [ext] gateware fixed point, non-parity")
@@ -92,12 +96,34 @@ def parse():
     return args
 
 
-def workload_config(n_gpus, frames):
-    return {"workload": WORKLOAD % frames,
-            "frames_per_gpu": frames, "global_frames": frames * n_gpus, "height": H, "width": W, "subsampling": SUB,
-            "quality": QUALITY, "zrl_policy": ZRL, "unique_frames": min(UNIQUE_FRAMES, frames),
-            "parallelism": "frames sharded across %d GPU(s), no data-path collective" % n_gpus,
-            "l2": "input (%.2f GB per GPU) > L2 (126 MB): every step streams from HBM" % (frames * H * W * 3 / 1e9)}
+def shard(n_frames, world, rank):
+    """Contiguous frame range of `rank` (the rule of litejpeg_b200.shard_range)."""
+    return n_frames * rank // world, n_frames * (rank + 1) // world
+
+
+def k1_source_sha():
+    """Short hash of the sources K1 is built from (ties profiles/k1_traffic.json to the code it was captured on)."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "jpeg_encoder_gsoc2017_ishan-bansal_b200", "csrc")
+    for name in ("b2j_fused.cu", "b2j_fused_stream.cuh", "b2j_block.cuh", "b2j_math.cuh", "b2j_common.cuh"):
+        try:
+            h.update(open(os.path.join(d, name), "rb").read())
+        except OSError:
+            h.update(name.encode())
+    return h.hexdigest()[:12]
+
+
+def workload_config(n_gpus, frames, scaling="strong"):
+    total = frames if scaling == "strong" else frames * n_gpus
+    per = [shard(total, n_gpus, r)[1] - shard(total, n_gpus, r)[0] for r in range(n_gpus)]
+    return {"workload": (WORKLOAD % total) + (", sharded across %d GPUs" % n_gpus if n_gpus > 1 else ""),
+            "frames_per_gpu": max(per), "global_frames": total, "height": H, "width": W, "subsampling": SUB,
+            "quality": QUALITY, "zrl_policy": ZRL, "unique_frames": min(UNIQUE_FRAMES, total),
+            "parallelism": "frames [g*B/G, (g+1)*B/G) on GPU g of %d, no data-path collective" % n_gpus,
+            "l2": "input (%.2f GB per GPU) %s L2 (126 MB)%s" % (max(per) * H * W * 3 / 1e9, ">" if max(per) * H * W * 3 > 126e6 else "<=",
+                                                            ": every step streams from HBM" if max(per) * H * W * 3 > 126e6
+                                                            else "; an L2 flush (256 MB write) runs between the timed steps")}
 
 
 # ---------------------------------------------------------------------------------- CPU arm
@@ -152,15 +178,16 @@ def run_reference_arm(args):
     import importlib
     import litejpeg_b200  # noqa: F401  (only for the synthetic frame generator; no GPU work on this arm)
     synth = importlib.import_module("litejpeg_b200.synth")
-    n = max(1, min(CPU_SAMPLE_FRAMES * 1080 * 1920 // (H * W), args.frames))
+    total = args.frames if args.scaling == "strong" else args.frames * max(1, args.gpus)
+    n = max(1, min(CPU_SAMPLE_FRAMES * 1080 * 1920 // (H * W), total))
     frames = synth.batch(n, H, W, CONFIG_IDX, KIND, unique=min(UNIQUE_FRAMES, n))
     for _ in range(max(0, args.warmup - 1)):
         cpu_baseline(frames, 1)
     base, dt = cpu_baseline(frames, max(1, args.steps))
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.gpus, args.frames), "cpu_baseline": base,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus, args.frames, args.scaling), "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "CPU arm = plain-C port of the reference's Python model (oracle/c/b2j_oracle.c); the model itself "
                     "is Python-only, cannot travel to the GPU box and measures 0.069 Mpixel/s (BASELINE.md)"}
@@ -278,14 +305,30 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     all_cpus = bind_to_gpu_numa_node(_nvml_index(torch, local_rank))   # before the pinned buffers are allocated
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo")      # host-side waits that must not occupy the GPUs
     n_gpus = max(world, 1)
-    frames = args.frames
+    total_frames = args.frames if args.scaling == "strong" else args.frames * n_gpus
+    lo, hi = shard(total_frames, n_gpus, rank)
+    frames = hi - lo
+    if frames < 1:
+        raise RuntimeError("fewer frames (%d) than GPUs (%d)" % (total_frames, n_gpus))
 
-    # ---- synthetic input (seeded per rank so every GPU has its own batch), pinned on the host
-    host = torch.empty((frames, H, W, 3), dtype=torch.uint8).pin_memory()
-    synth.batch(frames, H, W, CONFIG_IDX + 100 * rank, KIND, unique=min(UNIQUE_FRAMES, frames), out=host)
+    # ---- synthetic input, pinned on the host: frame i of the batch is synthetic frame i % unique.  Rank 0
+    # holds the whole batch (the one-call end-to-end path starts from it), the others their shard.
+    uniq = min(UNIQUE_FRAMES, total_frames)
+    h_lo, h_hi = (0, total_frames) if rank == 0 else (lo, hi)
+    host_all = torch.empty((h_hi - h_lo, H, W, 3), dtype=torch.uint8).pin_memory()
+    made = {}
+    for i in range(h_lo, h_hi):
+        if i % uniq not in made:
+            host_all[i - h_lo] = synth.frame(H, W, CONFIG_IDX, i % uniq, KIND)
+            made[i % uniq] = i - h_lo
+        else:
+            host_all[i - h_lo] = host_all[made[i % uniq]]
+    host = host_all[lo - h_lo:hi - h_lo]
     rgb = host.to(dev, non_blocking=True)
     torch.cuda.synchronize()
 
@@ -309,9 +352,14 @@ def main():
     sp = stream.cuda_stream
     dref = ctypes.byref(desc)
 
+    flush = None
+    if frames * H * W * 3 <= 126e6 and not args.graph:          # input fits L2: flush it between the timed steps
+        flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)
+
     def step(ev=None):
         """One pass of the hot path: exactly the launches b2j_encode issues, with optional stage events."""
         nonlocal stream, sp
+        if flush is not None: flush.fill_(1)
         if ev: ev[0].record(stream)
         lj._lib.check(L.b2j_fused_block(rgb.data_ptr(), dref, qy_a, qc_a, coefs.data_ptr(), dct_flag, sp))
         if ev: ev[1].record(stream)
@@ -372,45 +420,61 @@ def main():
     barrier()
     if sampler:
         sampler.window(w0, time.perf_counter())
-    elapsed_ms = t_start.elapsed_time(t_end)
     stage_ms = [sum(e[i].elapsed_time(e[i + 1]) for e in evs) / args.steps for i in range(2)]
+    # the step's own time: K1 start to stuffing end (an L2 flush between steps, when there is one, is not part of it)
+    elapsed_ms = t_start.elapsed_time(t_end) if flush is None else sum(e[0].elapsed_time(e[2]) for e in evs)
     if world > 1:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
-    px_per_step = n_gpus * frames * H * W
+    px_per_step = total_frames * H * W
     value = px_per_step * args.steps / (elapsed_ms / 1e3) / 1e6
 
-    # ---- end to end through the host-buffer entry point of the C ABI
+    # ---- end to end through the host-buffer entry point of the C ABI: ONE call on rank 0 over the devices of
+    # all ranks (b2j_multi_encoder_encode_host), from the pinned host batch to JFIF bytes in pinned host memory.
+    # The other ranks wait on a host-side (gloo) barrier, so their GPUs are free for that call.
+    def host_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=host_group)
+
     e2e = None
     if not args.skip_e2e:
-        out_host = torch.empty((frames, cap), dtype=torch.uint8).pin_memory()
-        sizes_host = torch.empty((frames,), dtype=torch.int64)
-        henc = lj.JpegEncoder(SUB, quality=QUALITY, zrl=ZRL, out_cap=cap, dct=args.dct, restart_interval=args.restart)
-        fpc = max(1, 16 * 1080 * 1920 // (H * W))
-        for _ in range(2):
-            henc.encode_host(host, out_host, sizes_host, frames_per_chunk=fpc)
-        assert torch.equal(sizes_host, sz)
-        assert out_host[frames - 1, :int(sz[-1])].equal(out[frames - 1, :int(sz[-1])].cpu())
-        e_steps = max(3, min(args.steps, 10))
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e_steps):
-            henc.encode_host(host, out_host, sizes_host, frames_per_chunk=fpc)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if sampler:
-            sampler.window(t0, t0 + dt)
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": px_per_step * e_steps / dt / 1e6, "unit": UNIT,
-               "h2d_bytes_per_step": n_gpus * frames * H * W * 3, "d2h_bytes_per_step": n_gpus * (out_bytes + frames * 8),
-               "steps": e_steps, "ms_per_step": dt / e_steps * 1e3, "frames_per_chunk": fpc,
-               "api": "b2j_encoder_encode_host (pinned host RGB in, JFIF bytes in pinned host memory out; wall clock "
-                      "around the call, which returns when the last byte is on the host)"}
-        henc.close()
+        host_barrier()
+        if rank == 0:
+            fpc = max(1, 16 * 1080 * 1920 // (H * W))
+            devices = list(range(n_gpus)) if torch.cuda.device_count() >= n_gpus else [local_rank]
+            menc = lj.MultiGpuJpegEncoder(devices, H, W, SUB, quality=QUALITY, zrl=ZRL, dct=args.dct, restart_interval=args.restart,
+                                          out_cap=cap, frames_per_chunk=fpc)
+            out_host = torch.empty((total_frames, cap), dtype=torch.uint8).pin_memory()
+            sizes_host = torch.empty((total_frames,), dtype=torch.int64)
+            for _ in range(2):
+                menc.encode_host(host_all, out_host, sizes_host)
+            assert torch.equal(sizes_host[lo:hi], sz) and int(sizes_host.min()) > 0
+            assert out_host[hi - 1, :int(sz[-1])].equal(out[frames - 1, :int(sz[-1])].cpu())
+            e_steps = max(3, min(args.steps, 10))
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                menc.encode_host(host_all, out_host, sizes_host)
+            dt = time.perf_counter() - t0
+            if sampler:
+                sampler.window(t0, t0 + dt)
+            h2d_s = menc.h2d_seconds(host_all, repeats=3)            # only the host-to-device copies of the same call
+            menc.close()
+            h2d_bytes = total_frames * H * W * 3
+            all_out = int(sizes_host.sum())
+            frac = h2d_s / (dt / e_steps)
+            e2e = {"value": total_frames * H * W * e_steps / dt / 1e6, "unit": UNIT,
+                   "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": all_out + total_frames * 8,
+                   "steps": e_steps, "ms_per_step": dt / e_steps * 1e3, "frames_per_chunk": fpc, "devices": devices,
+                   "h2d_ceiling_gbs": h2d_bytes / h2d_s / 1e9, "h2d_only_ms": h2d_s * 1e3, "frac_of_h2d_ceiling": frac,
+                   "limiter": ("host-to-device copies (PCIe / host memory path): the call runs at %.0f %% of the time the copies "
+                               "alone take" % (100 * frac)) if frac >= 0.7 else
+                              "not the copies alone (%.0f %% of the call): kernels, device-to-host copies and host threads" % (100 * frac),
+                   "api": "b2j_multi_encoder_encode_host on rank 0 over %d device(s): one call, pinned host RGB of the whole batch "
+                          "in, JFIF bytes in pinned host memory out; wall clock around the call, which returns when the last "
+                          "byte is on the host" % len(devices)}
+        host_barrier()
     clocks = sampler.stop() if sampler else None
 
     if rank != 0:
@@ -430,21 +494,27 @@ def main():
     k1_bytes = int(padded_px * (3 + 2 * coef_per_px))   # 3 B/px RGB read + int16 coefficients written (9 / 7 / 6 B per padded px)
     k1_ms = stage_ms[0]
     achieved = k1_bytes / (k1_ms / 1e3) / 1e9
-    traffic = None
+    # dram bytes of one K1 launch from the ncu --set full capture of this workload (profiles/scripts/prof_full.sh writes
+    # the file together with a hash of the kernel sources; a capture of other sources is not reported)
+    traffic, traffic_note = None, None
     if args.config == "2" and KIND == "photo" and frames == FRAMES_PER_GPU and args.dct == "model":   # the capture's workload
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
+            if traffic.get("k1_source_sha") != k1_source_sha():
+                traffic_note = "profiles/k1_traffic.json was captured from other kernel sources (%s)" % traffic.get("k1_source_sha")
+                traffic = None
         except Exception:
             pass
     hv = {"444": "1,1", "422": "2,1", "420": "2,2"}[SUB]
-    roofline = {"kernel": "k_fused_tiled<%s> (K1: colour + chroma resampling + %s DCT + quantise + zig-zag)"
+    roofline = {"kernel": "k_fused_stream<%s> (K1: colour + chroma resampling + %s DCT + quantise + zig-zag)"
                           % (hv, "float64" if args.dct == "model" else "fixed-point"),
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "frac_of_nominal_8000": achieved / 8000.0,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms,
                 "traffic": traffic["bytes_per_launch"] if traffic else None,
-                "traffic_source": traffic.get("source") if traffic else None,
+                "traffic_source": traffic.get("source") if traffic else traffic_note,
+                "k1_source_sha": k1_source_sha(),
                 "share_of_step": k1_ms / sum(stage_ms),
                 "note": "K1 is issue-bound, not HBM-bound: the model's float64 DCT graph costs ~650 FP64-pipe and ~1400 "
                         "other instructions per 8x8 block-equivalent (DESIGN.md)"}
@@ -453,13 +523,13 @@ def main():
     if all_cpus:
         os.sched_setaffinity(0, all_cpus)            # the CPU leg uses every host thread
     if not args.skip_cpu_baseline and n_gpus == 1 and args.dct == "model" and not args.restart:        # reported on rank 0 at N = 1 only
-        base, _ = cpu_baseline(host, 2)
+        base, _ = cpu_baseline(host_all, 2)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(n_gpus, frames),
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(n_gpus, args.frames, args.scaling),
             "stage_ms": {"K1_fused_block": stage_ms[0], "K2_K3_K4_entropy_fused_and_stuffing": stage_ms[1]},
-            "output_bytes_per_step": out_bytes, "bits_per_pixel": out_bytes * 8 / (frames * H * W),
+            "output_bytes_per_step_rank0": out_bytes, "bits_per_pixel": out_bytes * 8 / (frames * H * W),
             "roofline": roofline, "cpu_baseline": base, "e2e": e2e,
             "gpu_launches": args.steps * int(L.b2j_encode_launch_count(dref)), "clocks": clocks}
     print(json.dumps(line))

@@ -60,6 +60,7 @@ extern "C" {
 #define B2J_FUSED_SIMPLE 1  /* one thread per 8x8 block straight from global memory (cross-check) */
 #define B2J_FUSED_TILED 2   /* CTA-wide shared-memory tiles, bulk-async loads, one thread per block */
 #define B2J_FUSED_STREAM 3  /* warp-private 32-pixel regions, 8 lanes per block, no CTA barriers */
+#define B2J_FUSED_WIDE 4    /* warp-private 256-pixel regions, one lane per block, no CTA barriers */
 /* OR-ed into `variant`: [ext] DCT in the gateware's fixed-point arithmetic
  * (litejpeg/core/new_dct6.py:171-396: its constants and shift points, the two
  * wiring slips :262-263 / :294 corrected, 32-bit sums) instead of the float64
@@ -269,6 +270,25 @@ int b2j_encoder_create(b2j_encoder **enc, const b2j_image_desc *desc, int qualit
 int b2j_encoder_encode_host(b2j_encoder *enc, const uint8_t *rgb_host, int32_t n_frames,
                             uint8_t *out_host, int64_t *sizes_host);
 int b2j_encoder_destroy(b2j_encoder *enc);
+
+/* One call, several GPUs of one box.  replaces: the per-image loop test/model/enc_frame.py:203-238
+ * (the unit that shards): frames [g*n/G, (g+1)*n/G) of the host batch are encoded on devices[g]
+ * (contiguous shards, no exchange between devices), each by a b2j_encoder driven from its own host
+ * thread, so copies and kernels of all devices overlap.  A device may be listed more than once.
+ * Buffers as for b2j_encoder_encode_host; pinned host memory must be portable
+ * (cudaHostAllocPortable / cudaHostRegisterPortable, or any pinned allocation under unified addressing).
+ * b2j_multi_encoder_h2d_probe issues only the host-to-device copies of such a call (`repeats` passes)
+ * and reports the wall-clock seconds of one pass: the copy ceiling of the box for this batch, against
+ * which an end-to-end rate can be judged. */
+typedef struct b2j_multi_encoder b2j_multi_encoder;
+int b2j_multi_encoder_create(b2j_multi_encoder **enc, const int32_t *devices, int32_t n_devices,
+                             const b2j_image_desc *desc, int quality, int zrl, int64_t out_cap,
+                             int32_t frames_per_chunk);
+int b2j_multi_encoder_encode_host(b2j_multi_encoder *enc, const uint8_t *rgb_host, int32_t n_frames,
+                                  uint8_t *out_host, int64_t *sizes_host);
+int b2j_multi_encoder_h2d_probe(b2j_multi_encoder *enc, const uint8_t *rgb_host, int32_t n_frames,
+                                int32_t repeats, double *seconds_per_pass);
+int b2j_multi_encoder_destroy(b2j_multi_encoder *enc);
 
 #ifdef __cplusplus
 }

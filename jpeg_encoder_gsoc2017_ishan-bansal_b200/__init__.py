@@ -11,7 +11,7 @@ from .core import (RGB2YCbCr, YCbCr2RGB, rgb2ycbcr_coefs, ycbcr2rgb_coefs, YCbCr
                    ZigZag, zigzag_order, zigzag_rom, RunLength, EntropyCoder, RLEMain, Huffman, BitPack)
 from . import model                                                    # noqa: F401
 from .ingest import to_rgb, read_image                                 # noqa: F401
-from .encoder import (JpegEncoder, ShardedJpegEncoder, shard_range, gather_sizes, gather_streams,   # noqa: F401
+from .encoder import (JpegEncoder, MultiGpuJpegEncoder, ShardedJpegEncoder, shard_range, gather_sizes, gather_streams,   # noqa: F401
                       band_plan, assemble_bands)
 
 __version__ = "0.1.0"

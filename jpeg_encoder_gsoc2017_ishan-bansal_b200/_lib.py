@@ -74,6 +74,10 @@ SIGNATURES = {
     "b2j_encoder_create": (c_int, [ctypes.POINTER(_P), _DESC, c_int, c_int, c_int64, c_int32]),
     "b2j_encoder_encode_host": (c_int, [_P, _P, c_int32, _P, _P]),
     "b2j_encoder_destroy": (c_int, [_P]),
+    "b2j_multi_encoder_create": (c_int, [ctypes.POINTER(_P), _P, c_int32, _DESC, c_int, c_int, c_int64, c_int32]),
+    "b2j_multi_encoder_encode_host": (c_int, [_P, _P, c_int32, _P, _P]),
+    "b2j_multi_encoder_h2d_probe": (c_int, [_P, _P, c_int32, c_int32, ctypes.POINTER(ctypes.c_double)]),
+    "b2j_multi_encoder_destroy": (c_int, [_P]),
 }
 
 # enums of include/b2j.h
@@ -91,7 +95,7 @@ def opt_restart(n):
     if not 0 <= n <= 32767:
         raise ValueError("restart_interval must be in 0..32767 MCUs")
     return n << 16
-FUSED = {"auto": 0, "simple": 1, "tiled": 2}
+FUSED = {"auto": 0, "simple": 1, "tiled": 2, "stream": 3, "wide": 4}
 
 _lib = None
 

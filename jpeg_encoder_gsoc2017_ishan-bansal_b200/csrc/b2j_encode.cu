@@ -1,6 +1,11 @@
 // The whole encode path on device buffers (b2j_encode) and the host-buffer
 // encoder object used for end-to-end measurements (b2j_encoder_*).
+#include <condition_variable>
+#include <chrono>
+#include <mutex>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "b2j_common.cuh"
 
@@ -94,6 +99,7 @@ extern "C" int b2j_encode(const uint8_t *rgb, const b2j_image_desc *desc, int qu
 // device output, workspace and pinned staging, so that H2D of chunk i+1, the
 // kernels of chunk i and D2H of chunk i-1 overlap (2 slots = double buffering).
 struct b2j_encoder {
+    int device;                   // the CUDA device everything below lives on
     b2j_image_desc desc;          // n_frames = frames per chunk
     int quality, zrl;
     int64_t out_cap;
@@ -106,8 +112,21 @@ struct b2j_encoder {
     int64_t *h_sizes[kSlots];
 };
 
+// Makes `device` current for the lifetime of the object (the encoder's buffers and streams
+// belong to the device it was created on; callers may have another one current).
+struct DeviceGuard {
+    int saved = -1;
+    bool switched = false;
+    explicit DeviceGuard(int device)
+    {
+        if (cudaGetDevice(&saved) == cudaSuccess && saved != device) switched = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(saved); }
+};
+
 static void encoder_free(b2j_encoder *e)
 {
+    DeviceGuard guard(e->device);
     for (int s = 0; s < b2j_encoder::kSlots; s++) {
         if (e->d_rgb[s]) cudaFree(e->d_rgb[s]);
         if (e->d_out[s]) cudaFree(e->d_out[s]);
@@ -139,6 +158,7 @@ extern "C" int b2j_encoder_create(b2j_encoder **enc, const b2j_image_desc *desc,
     b2j_encoder *e = new (std::nothrow) b2j_encoder();
     B2J_REQUIRE(e, B2J_E_ARG, "b2j_encoder_create: out of host memory");
     memset(e, 0, sizeof *e);
+    if (cudaGetDevice(&e->device) != cudaSuccess) { delete e; return cuda_fail(cudaGetLastError(), "b2j_encoder_create"); }
     e->desc = d; e->quality = quality; e->zrl = zrl; e->out_cap = out_cap;
     e->frame_bytes = (size_t)g.height * (size_t)g.width * 3;
     e->ws_bytes = b2j_encode_workspace_bytes_opts(&d, out_cap, zrl);
@@ -199,12 +219,25 @@ static int drain_slot(b2j_encoder *e, int s, int first_frame, int n, uint8_t *ou
     return B2J_OK;
 }
 
+static int encode_host_impl(b2j_encoder *e, const uint8_t *rgb_host, int32_t n_frames, uint8_t *out_host, int64_t *sizes_host);
+
 extern "C" int b2j_encoder_encode_host(b2j_encoder *enc, const uint8_t *rgb_host, int32_t n_frames, uint8_t *out_host,
                                        int64_t *sizes_host)
 {
     B2J_REQUIRE(enc && rgb_host && out_host && sizes_host, B2J_E_ARG, "b2j_encoder_encode_host: null pointer");
     B2J_REQUIRE(n_frames >= 1, B2J_E_ARG, "b2j_encoder_encode_host: n_frames must be >= 1");
-    b2j_encoder *e = enc;
+    DeviceGuard guard(enc->device);
+    for (int i = 0; i < n_frames; i++) sizes_host[i] = INT64_MIN;   // frames not reached after an error stay marked
+    const int rc = encode_host_impl(enc, rgb_host, n_frames, out_host, sizes_host);
+    if (rc != B2J_OK && rc != B2J_E_CAPACITY) {
+        // error in the middle of the pipeline: queued copies may still read rgb_host / write out_host
+        for (int s = 0; s < b2j_encoder::kSlots; s++) cudaStreamSynchronize(enc->stream[s]);
+    }
+    return rc;
+}
+
+static int encode_host_impl(b2j_encoder *e, const uint8_t *rgb_host, int32_t n_frames, uint8_t *out_host, int64_t *sizes_host)
+{
     const int fpc = e->desc.n_frames;
     const int n_chunks = (n_frames + fpc - 1) / fpc;
     int bad = 0;
@@ -245,4 +278,173 @@ extern "C" int b2j_encoder_encode_host(b2j_encoder *enc, const uint8_t *rgb_host
         return B2J_E_CAPACITY;
     }
     return B2J_OK;
+}
+
+// ---------------------------------------------------------------- one call, several GPUs
+// Frames [g * n / G, (g + 1) * n / G) of the host batch go to the g-th device of the list (the
+// contiguous-shard rule of SURVEY 8e; the unit that shards is the per-image loop
+// test/model/enc_frame.py:203-238).  One persistent host thread per device drives a b2j_encoder
+// there, so the H2D copies, kernels and D2H copies of all devices run concurrently; there is no
+// exchange between the devices.
+struct b2j_multi_encoder {
+    struct Worker {
+        int device = 0;
+        b2j_encoder *enc = nullptr;
+        std::thread thread;
+        // job (guarded by the owner's mutex)
+        int job = 0;                  // 0 idle, 1 encode, 2 copy probe, 3 quit
+        const uint8_t *rgb = nullptr;
+        uint8_t *out = nullptr;
+        int64_t *sizes = nullptr;
+        int n = 0, repeats = 0;
+        int rc = 0;
+        char err[256] = "";
+    };
+    std::vector<Worker> workers;
+    std::mutex mu;
+    std::condition_variable cv_job, cv_done;
+    int pending = 0;
+    size_t frame_bytes = 0;
+    int64_t out_cap = 0;
+};
+
+static void multi_worker_main(b2j_multi_encoder *m, int idx)
+{
+    b2j_multi_encoder::Worker &w = m->workers[idx];
+    cudaSetDevice(w.device);
+    for (;;) {
+        int job;
+        {
+            std::unique_lock<std::mutex> lk(m->mu);
+            m->cv_job.wait(lk, [&] { return w.job != 0; });
+            job = w.job;
+        }
+        int rc = B2J_OK;
+        if (job == 1) {
+            rc = w.n > 0 ? b2j_encoder_encode_host(w.enc, w.rgb, w.n, w.out, w.sizes) : B2J_OK;
+        } else if (job == 2) {
+            // the H2D copies encode_host would issue, and nothing else
+            b2j_encoder *e = w.enc;
+            const int fpc = e->desc.n_frames;
+            for (int r = 0; r < w.repeats && rc == B2J_OK; r++) {
+                for (int first = 0, c = 0; first < w.n; first += fpc, c++) {
+                    const int n = w.n - first < fpc ? w.n - first : fpc;
+                    const int s = c % b2j_encoder::kSlots;
+                    cudaError_t e2 = cudaMemcpyAsync(e->d_rgb[s], w.rgb + (size_t)first * e->frame_bytes, (size_t)n * e->frame_bytes,
+                                                     cudaMemcpyHostToDevice, e->stream[s]);
+                    if (e2 != cudaSuccess) { rc = cuda_fail(e2, "b2j_multi_encoder_h2d_probe"); break; }
+                }
+                for (int s = 0; s < b2j_encoder::kSlots; s++) cudaStreamSynchronize(e->stream[s]);
+            }
+        }
+        if (rc) b2j_last_error(w.err, sizeof w.err);
+        {
+            std::lock_guard<std::mutex> lk(m->mu);
+            w.rc = rc;
+            w.job = 0;
+            m->pending--;
+        }
+        m->cv_done.notify_all();
+        if (job == 3) return;
+    }
+}
+
+// Hands `job` to every worker and waits for all of them; returns the first non-zero return code.
+static int multi_run(b2j_multi_encoder *m, int job)
+{
+    {
+        std::lock_guard<std::mutex> lk(m->mu);
+        for (auto &w : m->workers) w.job = job;
+        m->pending = (int)m->workers.size();
+    }
+    m->cv_job.notify_all();
+    std::unique_lock<std::mutex> lk(m->mu);
+    m->cv_done.wait(lk, [&] { return m->pending == 0; });
+    int rc = B2J_OK;
+    for (auto &w : m->workers)
+        if (w.rc && (rc == B2J_OK || rc == B2J_E_CAPACITY)) {
+            rc = w.rc;
+            set_error("device %d: %s", w.device, w.err);
+        }
+    return rc;
+}
+
+static void multi_shard(b2j_multi_encoder *m, const uint8_t *rgb_host, int32_t n_frames, uint8_t *out_host, int64_t *sizes_host)
+{
+    const long long G = (long long)m->workers.size();
+    for (long long g = 0; g < G; g++) {
+        const long long lo = g * n_frames / G, hi = (g + 1) * n_frames / G;
+        b2j_multi_encoder::Worker &w = m->workers[(size_t)g];
+        w.rgb = rgb_host + (size_t)lo * m->frame_bytes;
+        w.out = out_host ? out_host + (size_t)lo * (size_t)m->out_cap : nullptr;
+        w.sizes = sizes_host ? sizes_host + lo : nullptr;
+        w.n = (int)(hi - lo);
+    }
+}
+
+extern "C" int b2j_multi_encoder_destroy(b2j_multi_encoder *enc)
+{
+    if (!enc) return B2J_OK;
+    bool threads = false;
+    for (auto &w : enc->workers) threads = threads || w.thread.joinable();
+    if (threads) {
+        multi_run(enc, 3);
+        for (auto &w : enc->workers)
+            if (w.thread.joinable()) w.thread.join();
+    }
+    for (auto &w : enc->workers)
+        if (w.enc) encoder_free(w.enc);
+    delete enc;
+    return B2J_OK;
+}
+
+extern "C" int b2j_multi_encoder_create(b2j_multi_encoder **enc, const int32_t *devices, int32_t n_devices,
+                                        const b2j_image_desc *desc, int quality, int zrl, int64_t out_cap, int32_t frames_per_chunk)
+{
+    B2J_REQUIRE(enc && devices && desc, B2J_E_ARG, "b2j_multi_encoder_create: null pointer");
+    B2J_REQUIRE(n_devices >= 1 && n_devices <= 64, B2J_E_ARG, "b2j_multi_encoder_create: n_devices %d not in 1..64", n_devices);
+    int count = 0;
+    B2J_CUDA(cudaGetDeviceCount(&count));
+    for (int i = 0; i < n_devices; i++)
+        B2J_REQUIRE(devices[i] >= 0 && devices[i] < count, B2J_E_ARG, "b2j_multi_encoder_create: device %d of %d", devices[i], count);
+    b2j_multi_encoder *m = new (std::nothrow) b2j_multi_encoder();
+    B2J_REQUIRE(m, B2J_E_ARG, "b2j_multi_encoder_create: out of host memory");
+    m->workers.resize((size_t)n_devices);
+    int saved = 0;
+    cudaGetDevice(&saved);
+    int rc = B2J_OK;
+    for (int i = 0; i < n_devices && rc == B2J_OK; i++) {         // (a device may be listed more than once: two workers share it)
+        m->workers[(size_t)i].device = devices[i];
+        cudaError_t e = cudaSetDevice(devices[i]);
+        rc = e != cudaSuccess ? cuda_fail(e, "cudaSetDevice") : b2j_encoder_create(&m->workers[(size_t)i].enc, desc, quality, zrl, out_cap, frames_per_chunk);
+    }
+    cudaSetDevice(saved);
+    if (rc) { b2j_multi_encoder_destroy(m); return rc; }
+    m->frame_bytes = m->workers[0].enc->frame_bytes;
+    m->out_cap = m->workers[0].enc->out_cap;
+    for (int i = 0; i < n_devices; i++) m->workers[(size_t)i].thread = std::thread(multi_worker_main, m, i);
+    *enc = m;
+    return B2J_OK;
+}
+
+extern "C" int b2j_multi_encoder_encode_host(b2j_multi_encoder *enc, const uint8_t *rgb_host, int32_t n_frames, uint8_t *out_host,
+                                             int64_t *sizes_host)
+{
+    B2J_REQUIRE(enc && rgb_host && out_host && sizes_host, B2J_E_ARG, "b2j_multi_encoder_encode_host: null pointer");
+    B2J_REQUIRE(n_frames >= 1, B2J_E_ARG, "b2j_multi_encoder_encode_host: n_frames must be >= 1");
+    multi_shard(enc, rgb_host, n_frames, out_host, sizes_host);
+    return multi_run(enc, 1);
+}
+
+extern "C" int b2j_multi_encoder_h2d_probe(b2j_multi_encoder *enc, const uint8_t *rgb_host, int32_t n_frames, int32_t repeats,
+                                           double *seconds_per_pass)
+{
+    B2J_REQUIRE(enc && rgb_host && seconds_per_pass, B2J_E_ARG, "b2j_multi_encoder_h2d_probe: null pointer");
+    B2J_REQUIRE(n_frames >= 1 && repeats >= 1, B2J_E_ARG, "b2j_multi_encoder_h2d_probe: n_frames and repeats must be >= 1");
+    multi_shard(enc, rgb_host, n_frames, nullptr, nullptr);
+    for (auto &w : enc->workers) w.repeats = repeats;
+    const auto t0 = std::chrono::steady_clock::now();
+    const int rc = multi_run(enc, 2);
+    *seconds_per_pass = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / repeats;
+    return rc;
 }

@@ -396,6 +396,7 @@ __global__ void __launch_bounds__(kThreads, B2J_K1_MIN_CTAS) k_fused_tiled(const
 
 }  // namespace b2j
 #include "b2j_fused_stream.cuh"     // =========================================================== stream variant
+#include "b2j_fused_wide.cuh"       // =========================================================== wide variant
 namespace b2j {
 
 // Device attributes and occupancy are looked up once per device and kernel instantiation (the
@@ -459,6 +460,25 @@ static int launch_fused(const FusedParams &P0, const Geo &g, int variant, cudaSt
         B2J_LAUNCH_CHECK("k_fused_simple");
         return B2J_OK;
     }
+    if (variant == B2J_FUSED_WIDE) {
+        using WS = WideShape<H, V>;
+        const int regions_x = (g.mcus_x * 8 * H + WS::kRegW - 1) / WS::kRegW;
+        const long long n_regions = (long long)regions_x * g.mcus_y * g.n_frames;
+        if (n_regions < 0xFFF00000LL) {
+            static LaunchInfo cache[kMaxDevices];
+            LaunchInfo li;
+            int rc = launch_info(k_fused_wide<H, V, FIXED>, kWideThreads, WS::kSmem, cache, &li);
+            if (rc) return rc;
+            const long long ctas_needed = (n_regions + kWideWarps - 1) / kWideWarps;
+            const long long grid = ctas_needed < (long long)li.per_sm * li.sms ? ctas_needed : (long long)li.per_sm * li.sms;
+            CUtensorMap map;
+            if (!make_frame_map(P, WS::kSubPitch, WS::kRows, &map)) P.aligned = 0;
+            k_fused_wide<H, V, FIXED><<<(unsigned)grid, kWideThreads, WS::kSmem, st>>>(P, map, (unsigned)n_regions, regions_x);
+            B2J_LAUNCH_CHECK("k_fused_wide");
+            return B2J_OK;
+        }
+        variant = B2J_FUSED_TILED;
+    }
     if (variant == B2J_FUSED_STREAM) {
         using SS = StreamShape<H, V>;
         const int regions_x = (g.mcus_x * 8 * H + SS::kRegW - 1) / SS::kRegW;
@@ -501,7 +521,7 @@ extern "C" int b2j_fused_block(const uint8_t *rgb, const b2j_image_desc *desc, c
     B2J_REQUIRE(rgb && coefs && qy_host && qc_host, B2J_E_ARG, "b2j_fused_block: null pointer");
     const bool fixed = (variant & B2J_FUSED_DCT_FIXED) != 0;
     variant &= ~B2J_FUSED_DCT_FIXED;
-    B2J_REQUIRE(variant >= B2J_FUSED_AUTO && variant <= B2J_FUSED_STREAM, B2J_E_ARG, "b2j_fused_block: bad variant %d", variant);
+    B2J_REQUIRE(variant >= B2J_FUSED_AUTO && variant <= B2J_FUSED_WIDE, B2J_E_ARG, "b2j_fused_block: bad variant %d", variant);
     B2J_REQUIRE(((uintptr_t)coefs & 15) == 0, B2J_E_ALIGN, "b2j_fused_block: coefs must be 16-byte aligned");
     Geo g;
     int rc = make_geo(desc, &g);

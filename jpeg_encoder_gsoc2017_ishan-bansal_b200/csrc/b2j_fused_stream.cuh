@@ -32,8 +32,12 @@ namespace b2j {
 #define B2J_STREAM_THREADS 256
 #endif
 #ifndef B2J_STREAM_MIN_CTAS
-#define B2J_STREAM_MIN_CTAS 4
+#define B2J_STREAM_MIN_CTAS 3
 #endif
+#ifndef B2J_STREAM_UNROLL_A
+#define B2J_STREAM_UNROLL_A 1
+#endif
+constexpr int kStreamUnrollA = B2J_STREAM_UNROLL_A;
 constexpr int kStreamThreads = B2J_STREAM_THREADS;
 constexpr int kStreamWarps = kStreamThreads / 32;
 
@@ -229,7 +233,7 @@ k_fused_stream(const __grid_constant__ FusedParams P, const __grid_constant__ CU
         __syncwarp();
 
         // ---------------- phase A: colour conversion + subsampling; item = 4 pixels x V rows
-#pragma unroll 1
+#pragma unroll kStreamUnrollA
         for (int item = lane; item < 64; item += 32) {
             // the +128 of the chroma sums as a register addend of the first multiply-add (as a literal the
             // compiler turns it into a separate XOR per sum)

@@ -119,6 +119,8 @@ class JpegEncoder:
         self._ws = {}
         self._host = {}
 
+    MAX_WORKSPACES = 4
+
     # ------------------------------------------------------------------ helpers
     def desc_for(self, rgb):
         if rgb.dtype != torch.uint8 or rgb.dim() not in (3, 4) or rgb.shape[-1] != 3:
@@ -132,16 +134,23 @@ class JpegEncoder:
     def _cap(self, desc):
         return int(self.out_cap or _lib.lib().b2j_default_out_cap(ctypes.byref(desc)))
 
-    def _workspace(self, desc, device):
+    def _workspace(self, desc, device, stream=None):
+        """Workspace of one in-flight call.  It holds the ticket, the chunk status words and the packed
+        stream, so two calls that may overlap must not share it: it is keyed by the stream as well
+        as by the shape.  A few are kept; before an older one is dropped the device is synchronised
+        (a kernel on another stream may still be using it)."""
         cap = self._cap(desc)
-        key = (desc.height, desc.width, desc.n_frames, cap, str(device), self._opts)
+        key = (desc.height, desc.width, desc.n_frames, cap, str(device), self._opts, stream_ptr(stream) or 0)
         ws = self._ws.get(key)
         if ws is None:
             nbytes = _lib.lib().b2j_encode_workspace_bytes_opts(ctypes.byref(desc), cap, self._opts)
             if nbytes == 0:
                 raise _lib.B2JError(-1, _lib.last_error())
+            if len(self._ws) >= self.MAX_WORKSPACES:
+                torch.cuda.synchronize(device)
+                self._ws = {}
             ws = torch.empty((nbytes,), dtype=torch.uint8, device=device)
-            self._ws = {key: ws}            # keep one shape resident
+            self._ws[key] = ws
         return ws, cap
 
     # ------------------------------------------------------------------ device path
@@ -162,17 +171,25 @@ class JpegEncoder:
 
     def encode_device(self, rgb, out=None, sizes=None, stream=None):
         """K1..K4 on device buffers, asynchronous.  Returns (out (N, cap) uint8, sizes (N,) int64);
-        sizes[i] < 0 means slot i was too small (|sizes[i]| bytes are needed)."""
+        sizes[i] < 0 means slot i was too small (|sizes[i]| bytes are needed).
+        Calls on different streams use different workspaces and may overlap; calls on one stream
+        are ordered by the stream.  `out` / `sizes`, when given, must have exactly the shapes above."""
         require_cuda()
         if not rgb.is_cuda:
             raise ValueError("rgb must be a CUDA tensor")
         rgb = rgb.contiguous()
         desc = self.desc_for(rgb)
-        ws, cap = self._workspace(desc, rgb.device)
+        ws, cap = self._workspace(desc, rgb.device, stream)
         if out is None:
             out = torch.empty((desc.n_frames, cap), dtype=torch.uint8, device=rgb.device)
+        elif (out.dtype != torch.uint8 or tuple(out.shape) != (desc.n_frames, cap) or out.device != rgb.device
+              or not out.is_contiguous()):
+            raise ValueError("out must be a contiguous uint8 tensor of shape (%d, %d) on %s" % (desc.n_frames, cap, rgb.device))
         if sizes is None:
             sizes = torch.empty((desc.n_frames,), dtype=torch.int64, device=rgb.device)
+        elif (sizes.dtype != torch.int64 or tuple(sizes.shape) != (desc.n_frames,) or sizes.device != rgb.device
+              or not sizes.is_contiguous()):
+            raise ValueError("sizes must be a contiguous int64 tensor of shape (%d,) on %s" % (desc.n_frames, rgb.device))
         with torch.cuda.device(rgb.device):
             _lib.check(_lib.lib().b2j_encode(rgb.data_ptr(), ctypes.byref(desc), self.quality, _lib.table_arg(self.qy),
                                               _lib.table_arg(self.qc), self._opts, ws.data_ptr(),
@@ -259,6 +276,70 @@ class JpegEncoder:
         for enc in self._host.values():
             _lib.lib().b2j_encoder_destroy(enc)
         self._host = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------- multi-GPU (one process, one call)
+class MultiGpuJpegEncoder:
+    """[ext] One host batch, several GPUs of one box, ONE call (C entry b2j_multi_encoder_*): frames
+    shard_range(N, G, g) are encoded on devices[g], each device driven by its own host thread inside
+    the library; no exchange between devices.  The unit that shards is the per-image loop
+    test/model/enc_frame.py:203-238."""
+
+    def __init__(self, devices, height, width, subsampling="420", quality=75, zrl="eager", dct="model", restart_interval=0,
+                 out_cap=None, frames_per_chunk=16):
+        require_cuda()
+        self.devices = [int(d) for d in devices]
+        if not self.devices:
+            raise ValueError("at least one device")
+        self.subsampling = str(subsampling)
+        self.height, self.width = int(height), int(width)
+        opts = _lib.ZRL[zrl] | _lib.DCT_MODE[dct] | _lib.opt_restart(restart_interval)
+        d1 = _lib.make_desc(self.height, self.width, self.subsampling, int(frames_per_chunk))
+        self.out_cap = int(out_cap or _lib.lib().b2j_default_out_cap(ctypes.byref(_lib.make_desc(self.height, self.width, self.subsampling, 1))))
+        arr = (ctypes.c_int32 * len(self.devices))(*self.devices)
+        self._h = ctypes.c_void_p()
+        _lib.check(_lib.lib().b2j_multi_encoder_create(ctypes.byref(self._h), arr, len(self.devices), ctypes.byref(d1),
+                                                        int(quality), opts, self.out_cap, int(frames_per_chunk)))
+
+    def _check(self, rgb_host):
+        if rgb_host.is_cuda or rgb_host.dtype != torch.uint8 or rgb_host.dim() != 4 or \
+                tuple(rgb_host.shape[1:]) != (self.height, self.width, 3) or not rgb_host.is_contiguous():
+            raise ValueError("rgb_host must be a contiguous CPU uint8 tensor (N, %d, %d, 3)" % (self.height, self.width))
+
+    def encode_host(self, rgb_host, out_host=None, sizes_host=None):
+        """(N, H, W, 3) CPU uint8 (pinned for speed) -> (out_host (N, cap) uint8, sizes_host (N,) int64)."""
+        self._check(rgb_host)
+        n = rgb_host.shape[0]
+        if out_host is None:
+            out_host = torch.empty((n, self.out_cap), dtype=torch.uint8).pin_memory()
+        if sizes_host is None:
+            sizes_host = torch.empty((n,), dtype=torch.int64)
+        if tuple(out_host.shape) != (n, self.out_cap) or out_host.dtype != torch.uint8 or not out_host.is_contiguous() or \
+                tuple(sizes_host.shape) != (n,) or sizes_host.dtype != torch.int64:
+            raise ValueError("out_host must be (N, %d) uint8 and sizes_host (N,) int64" % self.out_cap)
+        _lib.check(_lib.lib().b2j_multi_encoder_encode_host(self._h, rgb_host.data_ptr(), n, out_host.data_ptr(),
+                                                             sizes_host.data_ptr()))
+        return out_host, sizes_host
+
+    def h2d_seconds(self, rgb_host, repeats=3):
+        """Wall-clock seconds of ONE pass of only the host-to-device copies encode_host would issue
+        (all devices concurrently): the copy ceiling of the box for this batch."""
+        self._check(rgb_host)
+        sec = ctypes.c_double()
+        _lib.check(_lib.lib().b2j_multi_encoder_h2d_probe(self._h, rgb_host.data_ptr(), rgb_host.shape[0], int(repeats),
+                                                           ctypes.byref(sec)))
+        return float(sec.value)
+
+    def close(self):
+        if self._h:
+            _lib.lib().b2j_multi_encoder_destroy(self._h)
+            self._h = ctypes.c_void_p()
 
     def __del__(self):
         try:

@@ -13,6 +13,7 @@ from oracle import model_np as M
 pytestmark = pytest.mark.gpu
 
 SUBS = ["444", "422", "420"]
+VARIANTS = ("simple", "tiled", "stream", "wide")      # every K1 kernel of b2j_fused_block (b2j.h B2J_FUSED_*)
 
 
 def synth(lj):
@@ -25,7 +26,7 @@ def test_lena_config1_coefficients_are_the_models(lj, golden):
     rgb = torch.from_numpy(golden.lena["rgb"]).cuda()
     enc = lj.JpegEncoder("444", tables=(M.y_quant_table.tolist(), M.cbcr_quant_table.tolist()))
     zz = golden.lena["zigzag"]
-    for variant in ("simple", "tiled"):
+    for variant in VARIANTS:
         coefs = enc.coefficients(rgb, variant=variant).cpu().numpy()[0].reshape(4096, 3, 64)
         for c in range(3):
             assert np.array_equal(coefs[:, c], zz[c]), (variant, c)
@@ -34,16 +35,18 @@ def test_lena_config1_coefficients_are_the_models(lj, golden):
 
 
 @pytest.mark.parametrize("sub", SUBS)
-@pytest.mark.parametrize("shape", [(8, 8), (16, 16), (37, 53), (96, 120), (64, 1040), (40, 2064), (17, 1025)])
+@pytest.mark.parametrize("shape", [(8, 8), (16, 16), (37, 53), (96, 120), (64, 1040), (40, 2064), (17, 1025), (33, 272), (24, 31),
+                                   (50, 544)])
 def test_coefficients_any_geometry(lj, oracle_c, sub, shape):
-    """Edge replication, ragged sides, several tiles per row, unaligned row strides."""
+    """Edge replication, ragged sides, several tiles / regions per row, unaligned row strides (widths that are
+    not a multiple of 16 bytes take the byte-wise loaders), widths around the 32- and 256-pixel regions."""
     h, w = shape
     g = torch.Generator().manual_seed(h * 10007 + w)
     rgb = torch.randint(0, 256, (2, h, w, 3), generator=g, dtype=torch.uint8)
     qy, qc = J.quant_tables(75)
     enc = lj.JpegEncoder(sub, quality=75)
     exp = np.stack([oracle_c.coefficients(rgb[i].numpy(), sub, qy, qc).reshape(-1, 64) for i in range(2)])
-    for variant in ("simple", "tiled"):
+    for variant in VARIANTS:
         got = enc.coefficients(rgb.cuda(), variant=variant).cpu().numpy()
         assert np.array_equal(got, exp), variant
 
@@ -240,6 +243,52 @@ def test_host_buffer_encoder_matches_device_path(lj, oracle_c):
     enc.close()
 
 
+def test_multi_device_encoder_one_call(lj, oracle_c):
+    """b2j_multi_encoder_*: one host batch sharded over a device list inside ONE call.  A 1-GPU box lists
+    device 0 several times (every entry gets its own worker thread, streams and buffers), which exercises
+    the same sharding, threading and joining code as N distinct GPUs."""
+    s = synth(lj)
+    n = 11
+    frames = torch.stack([s.frame(200, 328, 8, i) for i in range(n)]).pin_memory()
+    ref = [oracle_c.encode_jpeg(frames[i].numpy(), "420", 75, 0) for i in range(n)]
+    ndev = torch.cuda.device_count()
+    for devices in ([0], [0, 0, 0], list(range(ndev)) * 2):
+        enc = lj.MultiGpuJpegEncoder(devices, 200, 328, "420", quality=75, frames_per_chunk=2)
+        for _ in range(2):
+            out, sizes = enc.encode_host(frames)
+            for i in range(n):
+                assert out[i, :int(sizes[i])].numpy().tobytes() == ref[i], (devices, i)
+        few, fsz = enc.encode_host(frames[:2].contiguous())                 # fewer frames than workers: empty shards
+        assert few[1, :int(fsz[1])].numpy().tobytes() == ref[1]
+        assert enc.h2d_seconds(frames, repeats=2) > 0.0
+        enc.close()
+    with pytest.raises(lj.B2JError):
+        lj.MultiGpuJpegEncoder([ndev + 7], 200, 328)
+
+
+def test_one_encoder_on_two_streams(lj, oracle_c):
+    """one JpegEncoder used on two streams at once must not share a workspace between the calls."""
+    s = synth(lj)
+    a = torch.stack([s.frame(360, 640, 71, i) for i in range(6)]).cuda()
+    b = torch.stack([s.frame(360, 640, 72, i) for i in range(6)]).cuda()
+    ref_a = [oracle_c.encode_jpeg(a[i].cpu().numpy(), "420", 75, 0) for i in range(6)]
+    ref_b = [oracle_c.encode_jpeg(b[i].cpu().numpy(), "420", 75, 0) for i in range(6)]
+    enc = lj.JpegEncoder("420", quality=75)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for _ in range(4):
+        oa, za = enc.encode_device(a, stream=s1)
+        ob, zb = enc.encode_device(b, stream=s2)
+        torch.cuda.synchronize()
+        for i in range(6):
+            assert oa[i, :int(za[i])].cpu().numpy().tobytes() == ref_a[i]
+            assert ob[i, :int(zb[i])].cpu().numpy().tobytes() == ref_b[i]
+    with pytest.raises(ValueError):
+        enc.encode_device(a, out=torch.empty((6, 100), dtype=torch.uint8, device="cuda"))
+    with pytest.raises(ValueError):
+        enc.encode_device(a, sizes=torch.empty((5,), dtype=torch.int64, device="cuda"))
+
+
 def test_strided_input_through_the_c_abi(lj, oracle_c):
     """row_stride / frame_stride of b2j_image_desc: a crop of a larger device buffer, no copy."""
     s = synth(lj)
@@ -250,7 +299,8 @@ def test_strided_input_through_the_c_abi(lj, oracle_c):
     qy, qc = lj.quant_tables(75)
     coefs = torch.empty((1, g.blocks_per_frame, 64), dtype=torch.int16, device="cuda")
     base = big.data_ptr() + (y0 * 256 + x0) * 3
-    for variant in (1, 2):
+    for variant in (1, 2, 3, 4):
+        coefs.fill_(0x5A5A)
         lj._lib.check(lj.lib().b2j_fused_block(base, ctypes.byref(desc), lj._lib.table_arg(qy), lj._lib.table_arg(qc),
                                                coefs.data_ptr(), variant, torch.cuda.current_stream().cuda_stream))
         exp = oracle_c.coefficients(big[y0:y0 + crop_h, x0:x0 + crop_w].cpu().numpy(), "420", *J.quant_tables(75))
