@@ -290,6 +290,10 @@ def main():
     args = parse()
     if args.impl == "reference":
         return run_reference_arm(args)
+    # stdout carries exactly one JSON line: anything libraries print there meanwhile (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -532,7 +536,8 @@ def main():
             "output_bytes_per_step_rank0": out_bytes, "bits_per_pixel": out_bytes * 8 / (frames * H * W),
             "roofline": roofline, "cpu_baseline": base, "e2e": e2e,
             "gpu_launches": args.steps * int(L.b2j_encode_launch_count(dref)), "clocks": clocks}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -60,7 +60,6 @@ extern "C" {
 #define B2J_FUSED_SIMPLE 1  /* one thread per 8x8 block straight from global memory (cross-check) */
 #define B2J_FUSED_TILED 2   /* CTA-wide shared-memory tiles, bulk-async loads, one thread per block */
 #define B2J_FUSED_STREAM 3  /* warp-private 32-pixel regions, 8 lanes per block, no CTA barriers */
-#define B2J_FUSED_WIDE 4    /* warp-private 256-pixel regions, one lane per block, no CTA barriers */
 /* OR-ed into `variant`: [ext] DCT in the gateware's fixed-point arithmetic
  * (litejpeg/core/new_dct6.py:171-396: its constants and shift points, the two
  * wiring slips :262-263 / :294 corrected, 32-bit sums) instead of the float64

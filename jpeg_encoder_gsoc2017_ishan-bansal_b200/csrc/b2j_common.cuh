@@ -30,6 +30,32 @@ int cuda_fail(cudaError_t e, const char *what);
         if (e__ != cudaSuccess) return ::b2j::cuda_fail(e__, name);           \
     } while (0)
 
+// ---------------------------------------------------------------- launch geometry of persistent kernels
+// Device attributes and occupancy are looked up once per device and kernel instantiation (the
+// single-frame path is launch-latency bound: no attribute queries on the hot path).
+struct LaunchInfo {
+    int sms = 0, per_sm = 0;
+};
+static const int kMaxDevices = 64;
+
+template <class Kernel>
+static int launch_info(Kernel kernel, int threads, int smem, LaunchInfo *cache /*[kMaxDevices]*/, LaunchInfo *out)
+{
+    int dev = 0;
+    B2J_CUDA(cudaGetDevice(&dev));
+    const bool cached = dev >= 0 && dev < kMaxDevices;
+    LaunchInfo li = cached ? cache[dev] : LaunchInfo();
+    if (li.sms == 0) {
+        B2J_CUDA(cudaDeviceGetAttribute(&li.sms, cudaDevAttrMultiProcessorCount, dev));
+        B2J_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        B2J_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&li.per_sm, kernel, threads, smem));
+        if (li.per_sm < 1) li.per_sm = 1;
+        if (cached) cache[dev] = li;                               // benign race: every writer stores the same values
+    }
+    *out = li;
+    return B2J_OK;
+}
+
 // ---------------------------------------------------------------- geometry
 struct Geo {
     int width, height;            // source pixels

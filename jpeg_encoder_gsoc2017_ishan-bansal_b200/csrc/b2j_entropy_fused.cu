@@ -21,7 +21,6 @@
 //      written; 0xFF bytes are counted per 4096-byte chunk of the packed stream on the fly.
 // 0xFF stuffing, RSTm / EOI markers and JFIF framing then run on the packed stream (launch_stuffing).
 #include "b2j_entropy.cuh"
-#include <cstdlib>
 
 namespace b2j {
 
@@ -472,20 +471,16 @@ extern "C" int b2j_entropy_encode(const int16_t *coefs, const b2j_image_desc *de
     cudaStream_t st = as_stream(stream);
     B2J_CUDA(cudaMemsetAsync(ws, 0, status_bytes, st));              // ticket, error flag, chunk status words
     const long long total = (long long)chunks * nvf;
-    int dev = 0, sms = 148, per_sm = 1;
-    B2J_CUDA(cudaGetDevice(&dev));
-    B2J_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     using Kernel = void (*)(const FusedEntropyParams, const LutParam);
     const bool seg = sp.nseg > 1;
-    const Kernel kernel = zrl == B2J_ZRL_EAGER ? (seg ? (Kernel)k_entropy_fused<true, true> : (Kernel)k_entropy_fused<true, false>)
-                                               : (seg ? (Kernel)k_entropy_fused<false, true> : (Kernel)k_entropy_fused<false, false>);
-    B2J_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem));
-    B2J_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kChunk, kFusedSmem));
-    if (const char *cap = getenv("B2J_ENT_CTAS_PER_SM")) {              // tuning knob: leave room for a concurrent kernel
-        const int c = atoi(cap);
-        if (c >= 1 && c < per_sm) per_sm = c;
-    }
-    long long slots = (long long)sms * (per_sm < 1 ? 1 : per_sm);
+    const int which = (zrl == B2J_ZRL_EAGER ? 0 : 2) + (seg ? 1 : 0);
+    static const Kernel kernels[4] = {k_entropy_fused<true, false>, k_entropy_fused<true, true>, k_entropy_fused<false, false>,
+                                      k_entropy_fused<false, true>};
+    const Kernel kernel = kernels[which];
+    static LaunchInfo cache[4][kMaxDevices];                          // no attribute queries on the hot path
+    LaunchInfo li;
+    if ((rc = launch_info(kernel, kChunk, kFusedSmem, cache[which], &li))) return rc;
+    long long slots = (long long)li.sms * li.per_sm;
     if (slots > kMaxSlots) slots = kMaxSlots;
     const unsigned grid = (unsigned)(total < slots ? total : slots);   // persistent CTAs, one scratch slot each
     kernel<<<grid, kChunk, kFusedSmem, st>>>(P, L);

@@ -396,33 +396,7 @@ __global__ void __launch_bounds__(kThreads, B2J_K1_MIN_CTAS) k_fused_tiled(const
 
 }  // namespace b2j
 #include "b2j_fused_stream.cuh"     // =========================================================== stream variant
-#include "b2j_fused_wide.cuh"       // =========================================================== wide variant
 namespace b2j {
-
-// Device attributes and occupancy are looked up once per device and kernel instantiation (the
-// single-frame path is launch-latency bound).
-struct LaunchInfo {
-    int sms = 0, per_sm = 0;
-};
-static const int kMaxDevices = 64;
-
-template <class Kernel>
-static int launch_info(Kernel kernel, int threads, int smem, LaunchInfo *cache, LaunchInfo *out)
-{
-    int dev = 0;
-    B2J_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= kMaxDevices) dev = kMaxDevices - 1;                  // (not cached correctly beyond 64 devices: recomputed)
-    LaunchInfo li = cache[dev];
-    if (li.sms == 0 || dev == kMaxDevices - 1) {
-        B2J_CUDA(cudaDeviceGetAttribute(&li.sms, cudaDevAttrMultiProcessorCount, dev));
-        B2J_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        B2J_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&li.per_sm, kernel, threads, smem));
-        if (li.per_sm < 1) li.per_sm = 1;
-        cache[dev] = li;                                                       // benign race: every writer stores the same values
-    }
-    *out = li;
-    return B2J_OK;
-}
 
 // The frames as a [frame][row][byte] tensor for the stream kernel's region loads.  Returns false when the
 // layout cannot be described (unaligned base or strides, driver without the entry point): the kernel then
@@ -459,25 +433,6 @@ static int launch_fused(const FusedParams &P0, const Geo &g, int variant, cudaSt
         k_fused_simple<H, V, FIXED><<<(unsigned)((nblk + 127) / 128), 128, 0, st>>>(P);
         B2J_LAUNCH_CHECK("k_fused_simple");
         return B2J_OK;
-    }
-    if (variant == B2J_FUSED_WIDE) {
-        using WS = WideShape<H, V>;
-        const int regions_x = (g.mcus_x * 8 * H + WS::kRegW - 1) / WS::kRegW;
-        const long long n_regions = (long long)regions_x * g.mcus_y * g.n_frames;
-        if (n_regions < 0xFFF00000LL) {
-            static LaunchInfo cache[kMaxDevices];
-            LaunchInfo li;
-            int rc = launch_info(k_fused_wide<H, V, FIXED>, kWideThreads, WS::kSmem, cache, &li);
-            if (rc) return rc;
-            const long long ctas_needed = (n_regions + kWideWarps - 1) / kWideWarps;
-            const long long grid = ctas_needed < (long long)li.per_sm * li.sms ? ctas_needed : (long long)li.per_sm * li.sms;
-            CUtensorMap map;
-            if (!make_frame_map(P, WS::kSubPitch, WS::kRows, &map)) P.aligned = 0;
-            k_fused_wide<H, V, FIXED><<<(unsigned)grid, kWideThreads, WS::kSmem, st>>>(P, map, (unsigned)n_regions, regions_x);
-            B2J_LAUNCH_CHECK("k_fused_wide");
-            return B2J_OK;
-        }
-        variant = B2J_FUSED_TILED;
     }
     if (variant == B2J_FUSED_STREAM) {
         using SS = StreamShape<H, V>;
@@ -521,7 +476,7 @@ extern "C" int b2j_fused_block(const uint8_t *rgb, const b2j_image_desc *desc, c
     B2J_REQUIRE(rgb && coefs && qy_host && qc_host, B2J_E_ARG, "b2j_fused_block: null pointer");
     const bool fixed = (variant & B2J_FUSED_DCT_FIXED) != 0;
     variant &= ~B2J_FUSED_DCT_FIXED;
-    B2J_REQUIRE(variant >= B2J_FUSED_AUTO && variant <= B2J_FUSED_WIDE, B2J_E_ARG, "b2j_fused_block: bad variant %d", variant);
+    B2J_REQUIRE(variant >= B2J_FUSED_AUTO && variant <= B2J_FUSED_STREAM, B2J_E_ARG, "b2j_fused_block: bad variant %d", variant);
     B2J_REQUIRE(((uintptr_t)coefs & 15) == 0, B2J_E_ALIGN, "b2j_fused_block: coefs must be 16-byte aligned");
     Geo g;
     int rc = make_geo(desc, &g);

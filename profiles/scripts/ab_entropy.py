@@ -12,12 +12,16 @@ import litejpeg_b200 as lj                      # noqa: E402  (frame generator, 
 from litejpeg_b200 import _lib, synth           # noqa: E402
 
 N, H, W = 256, 1080, 1920
+libs = [a for a in sys.argv[1:] if not a.startswith("--")]
+for a in sys.argv[1:]:
+    if a.startswith("--n="):
+        N = int(a[4:])
 dev = torch.device("cuda:0")
-frames = synth.batch(N, H, W, 2, unique=32).to(dev)
+frames = synth.batch(N, H, W, 2, unique=min(N, 32)).to(dev)
 desc = _lib.make_desc(H, W, "420", N)
 P = ctypes.c_void_p
 for rnd in range(2):
-    for path in sys.argv[1:]:
+    for path in libs:
         L = ctypes.CDLL(os.path.abspath(path))
         L.b2j_default_out_cap.restype = ctypes.c_int64
         L.b2j_entropy_workspace_bytes.restype = ctypes.c_size_t
@@ -37,7 +41,8 @@ for rnd in range(2):
         sp = torch.cuda.current_stream().cuda_stream
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         t1 = t2 = 0.0
-        for it in range(13):
+        iters = 13 if N > 8 else 203
+        for it in range(iters):
             ev[0].record()
             assert L.b2j_fused_block(frames.data_ptr(), ctypes.byref(desc), qy, qc, coefs.data_ptr(), 0, sp) == 0
             ev[1].record()
@@ -47,5 +52,5 @@ for rnd in range(2):
             if it >= 3:
                 t1 += ev[0].elapsed_time(ev[1])
                 t2 += ev[1].elapsed_time(ev[2])
-        print("round %d  %-40s K1 %.4f ms  entropy+stuffing %.4f ms  bytes %d" % (rnd, os.path.basename(path), t1 / 10, t2 / 10, int(sizes.sum())), flush=True)
+        print("round %d  %-40s K1 %.4f ms  entropy+stuffing %.4f ms  bytes %d" % (rnd, os.path.basename(path), t1 / (iters - 3), t2 / (iters - 3), int(sizes.sum())), flush=True)
         del coefs, ws, out, sizes
