@@ -443,11 +443,16 @@ static int launch_fused(const FusedParams &P0, const Geo &g, int variant, cudaSt
             LaunchInfo li;
             int rc = launch_info(k_fused_stream<H, V, FIXED>, kStreamThreads, SS::kSmem, cache, &li);
             if (rc) return rc;
-            const long long ctas_needed = (n_regions + kStreamWarps - 1) / kStreamWarps;
+            // runs of regions per work item only when every resident warp still gets several items
+            const long long slots = (long long)li.per_sm * li.sms * kStreamWarps;
+            int run = (int)(n_regions / (slots * 4));
+            run = run < 1 ? 1 : (run > kStreamRun ? kStreamRun : run);
+            const long long n_items = n_regions / regions_x * ((regions_x + run - 1) / run);
+            const long long ctas_needed = (n_items + kStreamWarps - 1) / kStreamWarps;
             const long long grid = ctas_needed < (long long)li.per_sm * li.sms ? ctas_needed : (long long)li.per_sm * li.sms;
             CUtensorMap map;
             if (!make_frame_map(P, SS::kRawPitch, SS::kRows, &map)) P.aligned = 0;
-            k_fused_stream<H, V, FIXED><<<(unsigned)grid, kStreamThreads, SS::kSmem, st>>>(P, map, (unsigned)n_regions, regions_x);
+            k_fused_stream<H, V, FIXED><<<(unsigned)grid, kStreamThreads, SS::kSmem, st>>>(P, map, (unsigned)n_regions, regions_x, run);
             B2J_LAUNCH_CHECK("k_fused_stream");
             return B2J_OK;
         }

@@ -38,6 +38,10 @@ namespace b2j {
 #define B2J_STREAM_UNROLL_A 1
 #endif
 constexpr int kStreamUnrollA = B2J_STREAM_UNROLL_A;
+#ifndef B2J_STREAM_RUN
+#define B2J_STREAM_RUN 6
+#endif
+constexpr int kStreamRun = B2J_STREAM_RUN;        // regions per work item when there is work to spare
 constexpr int kStreamThreads = B2J_STREAM_THREADS;
 constexpr int kStreamWarps = kStreamThreads / 32;
 
@@ -92,12 +96,12 @@ __device__ __forceinline__ void stream_round(const uint8_t *src, uint8_t *t_row,
                                              const uint32_t (&stg_addr)[8], const uint32_t *mul8)
 {
     const uint2 px = *reinterpret_cast<const uint2 *>(src);
-    int s[8];
-    s[0] = (int)__byte_perm(px.x, 0u, 0x4440) - 128; s[1] = (int)__byte_perm(px.x, 0u, 0x4441) - 128;
-    s[2] = (int)__byte_perm(px.x, 0u, 0x4442) - 128; s[3] = (int)__byte_perm(px.x, 0u, 0x4443) - 128;
-    s[4] = (int)__byte_perm(px.y, 0u, 0x4440) - 128; s[5] = (int)__byte_perm(px.y, 0u, 0x4441) - 128;
-    s[6] = (int)__byte_perm(px.y, 0u, 0x4442) - 128; s[7] = (int)__byte_perm(px.y, 0u, 0x4443) - 128;
     if (FIXED) {
+        int s[8];
+        s[0] = (int)__byte_perm(px.x, 0u, 0x4440) - 128; s[1] = (int)__byte_perm(px.x, 0u, 0x4441) - 128;
+        s[2] = (int)__byte_perm(px.x, 0u, 0x4442) - 128; s[3] = (int)__byte_perm(px.x, 0u, 0x4443) - 128;
+        s[4] = (int)__byte_perm(px.y, 0u, 0x4440) - 128; s[5] = (int)__byte_perm(px.y, 0u, 0x4441) - 128;
+        s[6] = (int)__byte_perm(px.y, 0u, 0x4442) - 128; s[7] = (int)__byte_perm(px.y, 0u, 0x4443) - 128;
         dct_1d_fixed(s);
         int4 *o = reinterpret_cast<int4 *>(t_row);
         o[0] = make_int4(s[0], s[1], s[2], s[3]);
@@ -106,7 +110,16 @@ __device__ __forceinline__ void stream_round(const uint8_t *src, uint8_t *t_row,
         // row pass (enc_frame.py:92-100); outputs 0 and 4 are integers, exact as doubles
         int r0, r4;
         double r1, r2, r3, r5, r6, r7;
+#ifndef B2J_NO_PACKED_ROWS
+        dct_1d_bytes(px, r0, r4, r1, r2, r3, r5, r6, r7);
+#else
+        int s[8];
+        s[0] = (int)__byte_perm(px.x, 0u, 0x4440) - 128; s[1] = (int)__byte_perm(px.x, 0u, 0x4441) - 128;
+        s[2] = (int)__byte_perm(px.x, 0u, 0x4442) - 128; s[3] = (int)__byte_perm(px.x, 0u, 0x4443) - 128;
+        s[4] = (int)__byte_perm(px.y, 0u, 0x4440) - 128; s[5] = (int)__byte_perm(px.y, 0u, 0x4441) - 128;
+        s[6] = (int)__byte_perm(px.y, 0u, 0x4442) - 128; s[7] = (int)__byte_perm(px.y, 0u, 0x4443) - 128;
         dct_1d_int(s, r0, r4, r1, r2, r3, r5, r6, r7);
+#endif
         double2 *o = reinterpret_cast<double2 *>(t_row);
         o[0] = make_double2(i2d(r0), r1);
         o[1] = make_double2(r2, r3);
@@ -144,7 +157,8 @@ __device__ __forceinline__ void stream_round(const uint8_t *src, uint8_t *t_row,
 
 template <int H, int V, bool FIXED>
 __global__ void __launch_bounds__(kStreamThreads, B2J_STREAM_MIN_CTAS)
-k_fused_stream(const __grid_constant__ FusedParams P, const __grid_constant__ CUtensorMap tmap, unsigned n_regions, int regions_x)
+k_fused_stream(const __grid_constant__ FusedParams P, const __grid_constant__ CUtensorMap tmap, unsigned n_regions, int regions_x,
+               int kRun)
 {
     using SS = StreamShape<H, V>;
     constexpr int BPM = H * V + 2;
@@ -183,16 +197,22 @@ k_fused_stream(const __grid_constant__ FusedParams P, const __grid_constant__ CU
     const int oblk = lane >> 3, ochunk = lane & 7;                   // copy-out: block, 16-byte piece
     const uint4 *stg_out = reinterpret_cast<const uint4 *>(s_stg + oblk * 128 + ((((ochunk * 4) ^ kStgXor[oblk]) & 31) << 2));
 
-    // ---- region walk: r = (frame * mcus_y + my) * regions_x + rx, stepped by the number of warps
+    // ---- region walk.  A work item is a run of up to kRun consecutive regions of one MCU row (kRun: 1 when there
+    // are few regions per warp, e.g. a single frame; kStreamRun for batches); item
+    // q = (frame * mcus_y + my) * runs_x + run goes to warp q mod (number of warps).  Inside a run the next region is
+    // rx + 1 (a pointer increment); the item arithmetic runs once per run.
     const unsigned total_warps = gridDim.x * kStreamWarps;
-    unsigned r = blockIdx.x * kStreamWarps + warp;
-    if (r >= n_regions) return;
-    int rx = (int)(r % (unsigned)regions_x);
-    unsigned rowidx = r / (unsigned)regions_x;
+    const int runs_x = (regions_x + kRun - 1) / kRun;
+    const unsigned n_items = n_regions / (unsigned)regions_x * (unsigned)runs_x;
+    unsigned q = blockIdx.x * kStreamWarps + warp;
+    if (q >= n_items) return;
+    int run = (int)(q % (unsigned)runs_x);
+    unsigned rowidx = q / (unsigned)runs_x;
     int my = (int)(rowidx % (unsigned)P.mcus_y), frame = (int)(rowidx / (unsigned)P.mcus_y);
-    const int step_rx = (int)(total_warps % (unsigned)regions_x);
-    const unsigned step_rows = total_warps / (unsigned)regions_x;
+    const int step_run = (int)(total_warps % (unsigned)runs_x);
+    const unsigned step_rows = total_warps / (unsigned)runs_x;
     const int step_my = (int)(step_rows % (unsigned)P.mcus_y), step_frame = (int)(step_rows / (unsigned)P.mcus_y);
+    int rx = run * kRun, left = min(kRun, regions_x - rx);
 
     auto region_fast = [&](int rx_) { return P.aligned && (rx_ + 1) * SS::kRegW <= P.width; };
     // rows below the image and bytes right of it arrive as zeros (the former are replicated after landing)
@@ -241,9 +261,11 @@ k_fused_stream(const __grid_constant__ FusedParams P, const __grid_constant__ CU
             asm("mov.u32 %0, 0x80000000;" : "=r"(c_off));
             const int ry = item >> 3, grp = item & 7;
             uint32_t sy[V][4], scb[V][4], scr[V][4];
-            uint32_t cand = 0xFFFFFFFFu, cr_flag = 0u;
+            uint32_t cand[V], cr_flag[V];
 #pragma unroll
             for (int v = 0; v < V; v++) {
+                cand[v] = 0xFFFFFFFFu;
+                cr_flag[v] = 0u;
                 const uint32_t *q = reinterpret_cast<const uint32_t *>(raw + (ry * V + v) * SS::kRawPitch + grp * 12);
                 const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
                 uint32_t cr[4], cg[4], cb[4];
@@ -259,15 +281,24 @@ k_fused_stream(const __grid_constant__ FusedParams P, const __grid_constant__ CU
                     // inputs where the float64 model may differ from the exact value (b2j_math.cuh).  Luma
                     // candidates are rare (every grey pixel is one); Cr candidates (g == b, r - g even) are
                     // common, but only eight green values can really differ
-                    cand = min(cand, sy[v][i] & B2J_CONST_EXC_MASK);
-                    if ((scr[v][i] & B2J_CONST_EXC_MASK) == 0u) cr_flag |= s_crx[cg[i]];
+#ifndef B2J_NO_ROW_FLAGS
+                    cand[v] = min(cand[v], sy[v][i] & B2J_CONST_EXC_MASK);
+                    if ((scr[v][i] & B2J_CONST_EXC_MASK) == 0u) cr_flag[v] |= s_crx[cg[i]];
+#else
+                    cand[0] = min(cand[0], sy[v][i] & B2J_CONST_EXC_MASK);
+                    if ((scr[v][i] & B2J_CONST_EXC_MASK) == 0u) cr_flag[0] |= s_crx[cg[i]];
+#endif
                 }
             }
-            if (cand == 0u || cr_flag != 0u) {
-                // some pixel of the item is a candidate (every grey pixel is): patch the sums so that the
-                // top byte is the model's value.  Rare in photographic content.
 #pragma unroll
-                for (int v = 0; v < V; v++) {
+            for (int v = 0; v < V; v++) {
+#ifndef B2J_NO_ROW_FLAGS
+                if (cand[v] == 0u || cr_flag[v] != 0u) {
+#else
+                if (cand[0] == 0u || cr_flag[0] != 0u) {
+#endif
+                    // some pixel of this row of the item is a candidate (every grey pixel is): patch the sums so that
+                    // the top byte is the model's value.  Rare in photographic content.
                     const uint8_t *q = raw + (ry * V + v) * SS::kRawPitch + grp * 12;
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
@@ -307,17 +338,25 @@ k_fused_stream(const __grid_constant__ FusedParams P, const __grid_constant__ CU
 
         // ---------------- next region: coordinates, prefetch
         const int cur_frame = frame, cur_my = my, cur_rx = rx;
-        r += total_warps;
-        const bool more = r < n_regions && r >= total_warps;     // (wrap-around guard)
-        if (more) {
-            rx += step_rx;
-            const int carry = rx >= regions_x ? 1 : 0;
-            rx -= carry ? regions_x : 0;
-            my += step_my + carry;
-            frame += step_frame;
-            if (my >= P.mcus_y) { my -= P.mcus_y; frame++; }
-            if (region_fast(rx)) issue_load(frame, my, rx);
+        bool more = true;
+        if (left > 1) {
+            left--;
+            rx++;
+        } else {
+            q += total_warps;
+            more = q < n_items && q >= total_warps;                  // (wrap-around guard)
+            if (more) {
+                run += step_run;
+                const int carry = run >= runs_x ? 1 : 0;
+                run -= carry ? runs_x : 0;
+                my += step_my + carry;
+                frame += step_frame;
+                if (my >= P.mcus_y) { my -= P.mcus_y; frame++; }
+                rx = run * kRun;
+                left = min(kRun, regions_x - rx);
+            }
         }
+        if (more && region_fast(rx)) issue_load(frame, my, rx);
 
         // ---------------- phase B
         {

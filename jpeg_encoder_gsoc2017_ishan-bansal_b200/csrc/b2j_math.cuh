@@ -204,6 +204,52 @@ __device__ __forceinline__ void dct_1d_int(const int (&x)[8], int &r0, int &r4,
     r3 = __dmul_rn(B2J_SQRT2, e5);
 }
 
+// exact (double)(int16) of the low / high half of a word: one I2F.F64.S16 with a half-word selector
+__device__ __forceinline__ double half_lo_to_double(uint32_t w)
+{
+    double d;
+    asm("{.reg .b16 lo, hi; mov.b32 {lo, hi}, %1; cvt.rn.f64.s16 %0, lo;}" : "=d"(d) : "r"(w));
+    return d;
+}
+__device__ __forceinline__ double half_hi_to_double(uint32_t w)
+{
+    double d;
+    asm("{.reg .b16 lo, hi; mov.b32 {lo, hi}, %1; cvt.rn.f64.s16 %0, hi;}" : "=d"(d) : "r"(w));
+    return d;
+}
+
+// The same row transform straight from the eight sample BYTES of a row (px.x = samples 0..3, px.y = 4..7,
+// unsigned, the -128 level shift folded in): the integer butterflies of stages 1 and 2 run on pairs of 16-bit
+// fields (sums stay below 2^16; differences are two's complement halves whose low-half borrow is undone by
+// adding 0x8000 before the high half is read), and the int -> double conversions read the halves directly
+// (I2F.F64.S16 with a half-word selector).  17 integer instructions instead of 23; same values as dct_1d_int.
+__device__ __forceinline__ void dct_1d_bytes(uint2 px, int &r0, int &r4, double &r1, double &r2, double &r3,
+                                             double &r5, double &r6, double &r7)
+{
+    const uint32_t A1 = __byte_perm(px.x, 0u, 0x4140), A2 = __byte_perm(px.x, 0u, 0x4243);   // (x0, x1), (x3, x2)
+    const uint32_t B1 = __byte_perm(px.y, 0u, 0x4243), B2 = __byte_perm(px.y, 0u, 0x4140);   // (x7, x6), (x4, x5)
+    const uint32_t S1 = A1 + B1, S2 = A2 + B2;          // (a0, a1) + 256 each, (a3, a2) + 256 each
+    const uint32_t D1 = A1 - B1, D2 = A2 - B2;          // (a7, a6), (a4, a5)
+    const uint32_t T = S1 + S2, U = S1 - S2;            // (b0, b1) + 512 each, (b3, b2)
+    const uint32_t D1h = D1 + 0x8000u, D2h = D2 + 0x8000u, Uh = U + 0x8000u;
+    const int b0 = (int)(T & 0xFFFFu), b1 = (int)(T >> 16);
+    double b4, b7, b5, b6;
+    rot(half_lo_to_double(D2), half_lo_to_double(D1), B2J_C3, B2J_S3, b4, b7);          // a4, a7
+    rot(half_hi_to_double(D2h), half_hi_to_double(D1h), B2J_C1, B2J_S1, b5, b6);        // a5, a6
+    double e7 = __dadd_rn(b7, b5), e5 = __dsub_rn(b7, b5);
+    double e4 = __dadd_rn(b4, b6), e6 = __dsub_rn(b4, b6);
+    double f2, f3;
+    rot(half_hi_to_double(Uh), half_lo_to_double(U), B2J_C6, B2J_S6, f2, f3);           // b2, b3
+    r0 = b0 + b1 - 1024;
+    r4 = b0 - b1;
+    r2 = __dmul_rn(B2J_SQRT2, f2);
+    r6 = __dmul_rn(B2J_SQRT2, f3);
+    r1 = __dadd_rn(e7, e4);
+    r7 = __dsub_rn(e7, e4);
+    r5 = __dmul_rn(B2J_SQRT2, e6);
+    r3 = __dmul_rn(B2J_SQRT2, e5);
+}
+
 // [ext] "fixed" DCT mode: one pass of the gateware datapath
 // litejpeg/core/new_dct6.py:171-396 - its constants and shift points (:219-230, :345, :370),
 // every product floor(c * x / 2^s) - with the two wiring slips of the source (:262-263, :294)
