@@ -56,10 +56,14 @@ extern "C" {
 #define B2J_Q_RECIPROCAL 2  /* gateware, litejpeg/core/quantization.py:124-168 */
 
 /* variant of b2j_fused_block */
-#define B2J_FUSED_AUTO 0    /* the fastest variant (stream) */
+#define B2J_FUSED_AUTO 0    /* the fastest variant (pair) */
 #define B2J_FUSED_SIMPLE 1  /* one thread per 8x8 block straight from global memory (cross-check) */
 #define B2J_FUSED_TILED 2   /* CTA-wide shared-memory tiles, bulk-async loads, one thread per block */
 #define B2J_FUSED_STREAM 3  /* warp-private 32-pixel regions, 8 lanes per block, no CTA barriers */
+#define B2J_FUSED_PAIR 4    /* stream organisation, 64-pixel regions; DCT of two blocks per lane in packed float32 with an
+                             * error interval per coefficient and the exact float64 graph wherever the interval
+                             * straddles a step of the quantiser (same results as every other variant); falls back to
+                             * STREAM for B2J_FUSED_DCT_FIXED and for tables with a divisor 1 */
 /* OR-ed into `variant`: [ext] DCT in the gateware's fixed-point arithmetic
  * (litejpeg/core/new_dct6.py:171-396: its constants and shift points, the two
  * wiring slips :262-263 / :294 corrected, 32-bit sums) instead of the float64

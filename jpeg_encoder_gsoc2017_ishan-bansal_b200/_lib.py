@@ -95,7 +95,7 @@ def opt_restart(n):
     if not 0 <= n <= 32767:
         raise ValueError("restart_interval must be in 0..32767 MCUs")
     return n << 16
-FUSED = {"auto": 0, "simple": 1, "tiled": 2, "stream": 3}
+FUSED = {"auto": 0, "simple": 1, "tiled": 2, "stream": 3, "pair": 4}
 
 _lib = None
 

@@ -129,6 +129,25 @@ void make_quant_mul(const uint8_t *qy, const uint8_t *qc, QuantMul *qm)
     }
 }
 
+bool make_quant_f32(const uint8_t *qy, const uint8_t *qc, QuantF32 *qf)
+{
+    bool ok = true;
+    const double sqrt2 = 1.41421356237309504880;
+    for (int c = 0; c < 2; c++)
+        for (int x = 0; x < 8; x++)
+            for (int u = 0; u < 8; u++) {
+                const int i = x * 8 + u, d = c ? qc[i] : qy[i];
+                if (d < 2) ok = false;
+                const double s = ((x == 3 || x == 5) ? sqrt2 : 1.0) * ((u == 3 || u == 5) ? sqrt2 : 1.0);
+                const bool exact = (x & 3) == 0 && (u & 3) == 0;
+                const double h = ((d & 1) ? 0.5 : 0.0) - (exact ? 1.0 / 16 : 0.0), e = exact ? 0.0 : kFastPathErr;
+                qf->r[c][i] = (float)(s / (8.0 * (d ? d : 1)));
+                qf->ha[c][i] = (float)((h - e) * 8.0 / s);
+                qf->hb[c][i] = (float)((h + e) * 8.0 / s);
+            }
+    return ok;
+}
+
 static uint8_t *seg(uint8_t *p, int marker, const uint8_t *payload, int n)
 {
     *p++ = 0xFF; *p++ = (uint8_t)marker; *p++ = (uint8_t)((n + 2) >> 8); *p++ = (uint8_t)((n + 2) & 0xFF);

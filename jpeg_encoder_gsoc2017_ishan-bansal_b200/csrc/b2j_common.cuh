@@ -81,6 +81,19 @@ struct QuantMul {
 };
 void make_quant_mul(const uint8_t *qy, const uint8_t *qc, QuantMul *qm);
 
+// Constants of the single-precision fast path of K1 (b2j_fused_pair.cuh), per natural index x * 8 + u, in units of
+// the unscaled transform output `out` (v = out * s, s = sqrt2 for each of x, u in {3, 5}):
+//   r  = s / (8 d)                       y = sign * (|out| - H) * r, q = rint(y)
+//   ha = (h - e) * 8 / s, hb = (h + e) * 8 / s    the two ends of the error interval of |v / 8|
+// h = 1/2 for odd d (int() truncates before the model rounds), 0 for even d, less 1/16 for the four coefficients
+// that are exact multiples of 1/8 (e = 0 for them); e = kFastPathErr.  tests/test_fastpath_model.py derives the
+// bound and restates the arithmetic.  make_quant_f32 returns false when a divisor is 1 (fast path unsupported).
+static const double kFastPathErr = 1.0 / 1024;
+struct QuantF32 {
+    float r[2][64], ha[2][64], hb[2][64];
+};
+bool make_quant_f32(const uint8_t *qy, const uint8_t *qc, QuantF32 *qf);
+
 // ---------------------------------------------------------------- tables (host + device)
 // Zig-zag position of natural index i (enc_frame.py:131-139 / zigzag.py:19-27).
 #define B2J_ZIGZAG_INIT                                                         \

@@ -38,6 +38,7 @@ struct FusedParams {
     int n_frames;
     int aligned;                  // rows may use bulk-async copies
     QuantMul qm;
+    QuantF32 qf;                  // pair variant only
 };
 
 // =============================================================== simple variant
@@ -396,6 +397,7 @@ __global__ void __launch_bounds__(kThreads, B2J_K1_MIN_CTAS) k_fused_tiled(const
 
 }  // namespace b2j
 #include "b2j_fused_stream.cuh"     // =========================================================== stream variant
+#include "b2j_fused_pair.cuh"       // =========================================================== pair variant
 namespace b2j {
 
 // The frames as a [frame][row][byte] tensor for the stream kernel's region loads.  Returns false when the
@@ -434,6 +436,30 @@ static int launch_fused(const FusedParams &P0, const Geo &g, int variant, cudaSt
         B2J_LAUNCH_CHECK("k_fused_simple");
         return B2J_OK;
     }
+    if (variant == B2J_FUSED_PAIR && !FIXED) {
+        using SS = PairShape<H, V>;
+        const int regions_x = (g.mcus_x * 8 * H + SS::kRegW - 1) / SS::kRegW;
+        const long long n_regions = (long long)regions_x * g.mcus_y * g.n_frames;
+        if (n_regions < 0xFFF00000LL) {
+            static LaunchInfo cache[kMaxDevices];
+            LaunchInfo li;
+            int rc = launch_info(k_fused_pair<H, V>, kPairThreads, SS::kSmem, cache, &li);
+            if (rc) return rc;
+            const long long slots = (long long)li.per_sm * li.sms * kPairWarps;
+            int run = (int)(n_regions / (slots * 4));
+            run = run < 1 ? 1 : (run > kPairRun ? kPairRun : run);
+            const long long n_items = n_regions / regions_x * ((regions_x + run - 1) / run);
+            const long long ctas_needed = (n_items + kPairWarps - 1) / kPairWarps;
+            const long long grid = ctas_needed < (long long)li.per_sm * li.sms ? ctas_needed : (long long)li.per_sm * li.sms;
+            CUtensorMap map;
+            if (!make_frame_map(P, SS::kRawPitch, SS::kRows, &map)) P.aligned = 0;
+            k_fused_pair<H, V><<<(unsigned)grid, kPairThreads, SS::kSmem, st>>>(P, map, (unsigned)n_regions, regions_x, run);
+            B2J_LAUNCH_CHECK("k_fused_pair");
+            return B2J_OK;
+        }
+        variant = B2J_FUSED_STREAM;
+    }
+    if (variant == B2J_FUSED_PAIR) variant = B2J_FUSED_STREAM;      // (the gateware DCT has no single-precision path)
     if (variant == B2J_FUSED_STREAM) {
         using SS = StreamShape<H, V>;
         const int regions_x = (g.mcus_x * 8 * H + SS::kRegW - 1) / SS::kRegW;
@@ -481,7 +507,7 @@ extern "C" int b2j_fused_block(const uint8_t *rgb, const b2j_image_desc *desc, c
     B2J_REQUIRE(rgb && coefs && qy_host && qc_host, B2J_E_ARG, "b2j_fused_block: null pointer");
     const bool fixed = (variant & B2J_FUSED_DCT_FIXED) != 0;
     variant &= ~B2J_FUSED_DCT_FIXED;
-    B2J_REQUIRE(variant >= B2J_FUSED_AUTO && variant <= B2J_FUSED_STREAM, B2J_E_ARG, "b2j_fused_block: bad variant %d", variant);
+    B2J_REQUIRE(variant >= B2J_FUSED_AUTO && variant <= B2J_FUSED_PAIR, B2J_E_ARG, "b2j_fused_block: bad variant %d", variant);
     B2J_REQUIRE(((uintptr_t)coefs & 15) == 0, B2J_E_ALIGN, "b2j_fused_block: coefs must be 16-byte aligned");
     Geo g;
     int rc = make_geo(desc, &g);
@@ -494,11 +520,13 @@ extern "C" int b2j_fused_block(const uint8_t *rgb, const b2j_image_desc *desc, c
     P.width = g.width; P.height = g.height; P.mcus_x = g.mcus_x; P.mcus_y = g.mcus_y; P.n_frames = g.n_frames;
     P.aligned = (((uintptr_t)rgb & 15) == 0 && (g.row_stride & 15) == 0 && (g.frame_stride & 15) == 0) ? 1 : 0;
     make_quant_mul(qy_host, qc_host, &P.qm);
+    const bool fast_ok = make_quant_f32(qy_host, qc_host, &P.qf);
     cudaStream_t st = as_stream(stream);
 #ifndef B2J_FUSED_DEFAULT
-#define B2J_FUSED_DEFAULT B2J_FUSED_STREAM
+#define B2J_FUSED_DEFAULT B2J_FUSED_PAIR
 #endif
     if (variant == B2J_FUSED_AUTO) variant = B2J_FUSED_DEFAULT;
+    if (variant == B2J_FUSED_PAIR && !fast_ok) variant = B2J_FUSED_STREAM;    // a divisor 1: exact arithmetic throughout
     if (fixed) {
         if (g.h == 1) return launch_fused<1, 1, true>(P, g, variant, st);
         if (g.v == 1) return launch_fused<2, 1, true>(P, g, variant, st);

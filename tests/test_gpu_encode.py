@@ -13,7 +13,7 @@ from oracle import model_np as M
 pytestmark = pytest.mark.gpu
 
 SUBS = ["444", "422", "420"]
-VARIANTS = ("simple", "tiled", "stream")      # every K1 kernel of b2j_fused_block (b2j.h B2J_FUSED_*)
+VARIANTS = ("simple", "tiled", "stream", "pair")      # every K1 kernel of b2j_fused_block (b2j.h B2J_FUSED_*)
 
 
 def synth(lj):
@@ -299,7 +299,7 @@ def test_strided_input_through_the_c_abi(lj, oracle_c):
     qy, qc = lj.quant_tables(75)
     coefs = torch.empty((1, g.blocks_per_frame, 64), dtype=torch.int16, device="cuda")
     base = big.data_ptr() + (y0 * 256 + x0) * 3
-    for variant in (1, 2, 3):
+    for variant in (1, 2, 3, 4):
         coefs.fill_(0x5A5A)
         lj._lib.check(lj.lib().b2j_fused_block(base, ctypes.byref(desc), lj._lib.table_arg(qy), lj._lib.table_arg(qc),
                                                coefs.data_ptr(), variant, torch.cuda.current_stream().cuda_stream))
