@@ -106,7 +106,7 @@ def k1_source_sha():
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, "jpeg_encoder_gsoc2017_ishan-bansal_b200", "csrc")
-    for name in ("b2j_fused.cu", "b2j_fused_stream.cuh", "b2j_block.cuh", "b2j_math.cuh", "b2j_common.cuh"):
+    for name in ("b2j_fused.cu", "b2j_fused_pair.cuh", "b2j_fused_stream.cuh", "b2j_block.cuh", "b2j_math.cuh", "b2j_common.cuh"):
         try:
             h.update(open(os.path.join(d, name), "rb").read())
         except OSError:
@@ -510,8 +510,10 @@ def main():
         except Exception:
             pass
     hv = {"444": "1,1", "422": "2,1", "420": "2,2"}[SUB]
-    roofline = {"kernel": "k_fused_stream<%s> (K1: colour + chroma resampling + %s DCT + quantise + zig-zag)"
-                          % (hv, "float64" if args.dct == "model" else "fixed-point"),
+    pair = args.dct == "model" and min(int(x) for x in list(qy) + list(qc)) >= 2        # b2j.h B2J_FUSED_PAIR: what AUTO launches
+    roofline = {"kernel": "%s<%s> (K1: colour + chroma resampling + %s DCT + quantise + zig-zag)"
+                          % ("k_fused_pair" if pair else "k_fused_stream", hv,
+                             "float32-with-error-interval / exact float64" if pair else "float64" if args.dct == "model" else "fixed-point"),
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "frac_of_nominal_8000": achieved / 8000.0,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
@@ -520,8 +522,8 @@ def main():
                 "traffic_source": traffic.get("source") if traffic else traffic_note,
                 "k1_source_sha": k1_source_sha(),
                 "share_of_step": k1_ms / sum(stage_ms),
-                "note": "K1 is issue-bound, not HBM-bound: the model's float64 DCT graph costs ~650 FP64-pipe and ~1400 "
-                        "other instructions per 8x8 block-equivalent (DESIGN.md)"}
+                "note": "K1 is issue-bound, not HBM-bound: ~58 thread-instructions per pixel for the bit-exact colour "
+                        "conversion, DCT and quantiser (DESIGN.md, profiles/r02)"}
 
     base = None
     if all_cpus:

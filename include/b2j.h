@@ -70,6 +70,9 @@ extern "C" {
  * model.  NOT parity with the model (<= 4 LSB per coefficient before
  * quantisation); checked against its own restatement oracle/gateware.py. */
 #define B2J_FUSED_DCT_FIXED 0x100
+/* [test] OR-ed into B2J_FUSED_PAIR: widen the error interval of the single-precision path from 1/1024 to 1/4, so that
+ * nearly every round of blocks takes the exact float64 path (same results; exercises the recomputation). */
+#define B2J_FUSED_PAIR_WIDE 0x200
 /* The `zrl` argument of b2j_entropy_encode, b2j_encode and b2j_encoder_create is an option word:
  *   bits 0..7    B2J_ZRL_*
  *   bit  8       B2J_OPT_DCT_FIXED (b2j_encode / b2j_encoder_create: K1 uses B2J_FUSED_DCT_FIXED)
@@ -114,6 +117,12 @@ int b2j_get_geometry(const b2j_image_desc *desc, b2j_geometry *geo);
 /* [ext] IJG scaling of the Annex-K tables; quality 85 gives the model's tables
  * (test/model/enc_frame.py:141-159), 50 the gateware's (core/quantization.py:20-27). */
 int b2j_quant_tables(int quality, uint8_t qy_host[64], uint8_t qc_host[64]);
+/* Host only: the constants of K1's single-precision path (B2J_FUSED_PAIR) for a pair of tables, per natural index
+ * x * 8 + u and class (0 luma, 1 chroma): out[0] multipliers r, out[1] and out[2] the offsets of the upper and lower
+ * end of the error interval (csrc/b2j_common.cuh QuantF32; restated by tests/fastpath_model.py).  Returns 1 when the
+ * tables are supported by that path, 0 when a divisor is 1 (the exact variant is used), < 0 on error.
+ * replaces: the divider walk of quantize(), test/model/enc_frame.py:111-129, for that path. */
+int b2j_fastpath_constants(const uint8_t qy_host[64], const uint8_t qc_host[64], float out[3][2][64]);
 
 /* ---------------------------------------------------------------- K0: one kernel per stage operator */
 

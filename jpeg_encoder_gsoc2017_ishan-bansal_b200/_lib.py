@@ -43,6 +43,7 @@ SIGNATURES = {
     "b2j_last_error": (c_size_t, [ctypes.c_char_p, c_size_t]),
     "b2j_get_geometry": (c_int, [_DESC, ctypes.POINTER(Geometry)]),
     "b2j_quant_tables": (c_int, [c_int, _P, _P]),
+    "b2j_fastpath_constants": (c_int, [_P, _P, _P]),
     "b2j_rgb2ycbcr": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P]),
     "b2j_ycbcr444to422": (c_int, [_P, _P, _P, _P, _P, c_int64, _P]),
     "b2j_ycbcr2rgb": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
@@ -95,7 +96,7 @@ def opt_restart(n):
     if not 0 <= n <= 32767:
         raise ValueError("restart_interval must be in 0..32767 MCUs")
     return n << 16
-FUSED = {"auto": 0, "simple": 1, "tiled": 2, "stream": 3, "pair": 4}
+FUSED = {"auto": 0, "simple": 1, "tiled": 2, "stream": 3, "pair": 4, "pair_wide": 4 | 0x200}
 
 _lib = None
 

@@ -129,7 +129,7 @@ void make_quant_mul(const uint8_t *qy, const uint8_t *qc, QuantMul *qm)
     }
 }
 
-bool make_quant_f32(const uint8_t *qy, const uint8_t *qc, QuantF32 *qf)
+bool make_quant_f32(const uint8_t *qy, const uint8_t *qc, QuantF32 *qf, double err)
 {
     bool ok = true;
     const double sqrt2 = 1.41421356237309504880;
@@ -140,7 +140,7 @@ bool make_quant_f32(const uint8_t *qy, const uint8_t *qc, QuantF32 *qf)
                 if (d < 2) ok = false;
                 const double s = ((x == 3 || x == 5) ? sqrt2 : 1.0) * ((u == 3 || u == 5) ? sqrt2 : 1.0);
                 const bool exact = (x & 3) == 0 && (u & 3) == 0;
-                const double h = ((d & 1) ? 0.5 : 0.0) - (exact ? 1.0 / 16 : 0.0), e = exact ? 0.0 : kFastPathErr;
+                const double h = ((d & 1) ? 0.5 : 0.0) - (exact ? 1.0 / 16 : 0.0), e = exact ? 0.0 : err;
                 qf->r[c][i] = (float)(s / (8.0 * (d ? d : 1)));
                 qf->ha[c][i] = (float)((h - e) * 8.0 / s);
                 qf->hb[c][i] = (float)((h + e) * 8.0 / s);
@@ -221,6 +221,19 @@ extern "C" int b2j_get_geometry(const b2j_image_desc *desc, b2j_geometry *geo)
     geo->header_bytes = kHeaderBytes;
     geo->reserved = 0;
     return B2J_OK;
+}
+
+extern "C" int b2j_fastpath_constants(const uint8_t qy_host[64], const uint8_t qc_host[64], float out[3][2][64])
+{
+    B2J_REQUIRE(qy_host && qc_host && out, B2J_E_ARG, "b2j_fastpath_constants: null pointer");
+    for (int i = 0; i < 64; i++)
+        B2J_REQUIRE(qy_host[i] >= 1 && qc_host[i] >= 1, B2J_E_ARG, "b2j_fastpath_constants: zero quantiser at %d", i);
+    QuantF32 qf;
+    const bool ok = make_quant_f32(qy_host, qc_host, &qf);
+    memcpy(out[0], qf.r, sizeof qf.r);
+    memcpy(out[1], qf.ha, sizeof qf.ha);
+    memcpy(out[2], qf.hb, sizeof qf.hb);
+    return ok ? 1 : 0;
 }
 
 extern "C" int b2j_quant_tables(int quality, uint8_t qy_host[64], uint8_t qc_host[64])

@@ -92,7 +92,7 @@ static const double kFastPathErr = 1.0 / 1024;
 struct QuantF32 {
     float r[2][64], ha[2][64], hb[2][64];
 };
-bool make_quant_f32(const uint8_t *qy, const uint8_t *qc, QuantF32 *qf);
+bool make_quant_f32(const uint8_t *qy, const uint8_t *qc, QuantF32 *qf, double err = kFastPathErr);
 
 // ---------------------------------------------------------------- tables (host + device)
 // Zig-zag position of natural index i (enc_frame.py:131-139 / zigzag.py:19-27).

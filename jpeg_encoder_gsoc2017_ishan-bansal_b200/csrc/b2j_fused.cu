@@ -506,7 +506,8 @@ extern "C" int b2j_fused_block(const uint8_t *rgb, const b2j_image_desc *desc, c
 {
     B2J_REQUIRE(rgb && coefs && qy_host && qc_host, B2J_E_ARG, "b2j_fused_block: null pointer");
     const bool fixed = (variant & B2J_FUSED_DCT_FIXED) != 0;
-    variant &= ~B2J_FUSED_DCT_FIXED;
+    const bool wide = (variant & B2J_FUSED_PAIR_WIDE) != 0;
+    variant &= ~(B2J_FUSED_DCT_FIXED | B2J_FUSED_PAIR_WIDE);
     B2J_REQUIRE(variant >= B2J_FUSED_AUTO && variant <= B2J_FUSED_PAIR, B2J_E_ARG, "b2j_fused_block: bad variant %d", variant);
     B2J_REQUIRE(((uintptr_t)coefs & 15) == 0, B2J_E_ALIGN, "b2j_fused_block: coefs must be 16-byte aligned");
     Geo g;
@@ -520,7 +521,7 @@ extern "C" int b2j_fused_block(const uint8_t *rgb, const b2j_image_desc *desc, c
     P.width = g.width; P.height = g.height; P.mcus_x = g.mcus_x; P.mcus_y = g.mcus_y; P.n_frames = g.n_frames;
     P.aligned = (((uintptr_t)rgb & 15) == 0 && (g.row_stride & 15) == 0 && (g.frame_stride & 15) == 0) ? 1 : 0;
     make_quant_mul(qy_host, qc_host, &P.qm);
-    const bool fast_ok = make_quant_f32(qy_host, qc_host, &P.qf);
+    const bool fast_ok = make_quant_f32(qy_host, qc_host, &P.qf, wide ? 0.25 : kFastPathErr);
     cudaStream_t st = as_stream(stream);
 #ifndef B2J_FUSED_DEFAULT
 #define B2J_FUSED_DEFAULT B2J_FUSED_PAIR

@@ -5,7 +5,7 @@ TAG=${1:-r02}
 CMD="python bench.py --steps 2 --warmup 3 --skip-e2e --skip-cpu-baseline"
 mkdir -p gpurun_out
 $CMD > gpurun_out/plainfull2_$TAG.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"k_fused_stream|k_entropy_fused" -s 8 -c 2 -f -o gpurun_out/proffull_$TAG $CMD > gpurun_out/ncufull2_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_fused_pair|k_fused_stream|k_entropy_fused" -s 8 -c 2 -f -o gpurun_out/proffull_$TAG $CMD > gpurun_out/ncufull2_$TAG.log 2>&1
 tail -2 gpurun_out/ncufull2_$TAG.log | cut -c1-200
 ncu -i gpurun_out/proffull_$TAG.ncu-rep --page raw --csv > gpurun_out/proffull_${TAG}_raw.csv
 ncu -i gpurun_out/proffull_$TAG.ncu-rep --page source --csv --print-source sass > gpurun_out/proffull_${TAG}_sass.csv
@@ -22,7 +22,7 @@ def val(r, name):
     u = units[ix[name]]
     return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
 for r in rows[2:]:
-    if "k_fused_stream" in r[ix["Kernel Name"]]:
+    if "k_fused_pair" in r[ix["Kernel Name"]] or "k_fused_stream" in r[ix["Kernel Name"]]:
         rd, wr = val(r, "dram__bytes_read.sum"), val(r, "dram__bytes_write.sum")
         json.dump({"bytes_per_launch": int(rd + wr), "dram_bytes_read": int(rd), "dram_bytes_write": int(wr),
                    "k1_source_sha": bench.k1_source_sha(),

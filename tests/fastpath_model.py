@@ -20,7 +20,7 @@ PI = 3.14159265358979323846
 SQRT2 = 1.41421356237309504880
 
 # bound on |float32 transform / 8 - float64 transform / 8| the guard assumes (see tests/test_fastpath_model.py)
-E_A = 3.0 / 4096
+E_A = 1.0 / 1024
 MAGIC = 12582912.0          # 1.5 * 2^23: float32 ulp is 1 in [2^23, 2^24)
 
 

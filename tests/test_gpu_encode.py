@@ -13,7 +13,7 @@ from oracle import model_np as M
 pytestmark = pytest.mark.gpu
 
 SUBS = ["444", "422", "420"]
-VARIANTS = ("simple", "tiled", "stream", "pair")      # every K1 kernel of b2j_fused_block (b2j.h B2J_FUSED_*)
+VARIANTS = ("simple", "tiled", "stream", "pair", "pair_wide")      # every K1 kernel of b2j_fused_block (b2j.h B2J_FUSED_*)
 
 
 def synth(lj):
