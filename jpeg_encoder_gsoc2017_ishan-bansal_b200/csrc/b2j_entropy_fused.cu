@@ -2,10 +2,11 @@
 //
 // Persistent CTAs take chunks of 128 consecutive blocks of a stream by ticket (a stream is a frame,
 // or with [ext] restart intervals one segment of a frame; tickets interleave the streams):
-//   1. the chunk's coefficients (+ 8 lookahead blocks) are loaded once, coalesced, into
-//      shared memory (33-word pitch per block: conflict free both for the cooperative
-//      stores and for the per-thread reads); the loading thread also records which of its
-//      eight coefficients are non-zero, so every block gets its 64-bit non-zero mask;
+//   1. the chunk's coefficients (+ 8 lookahead blocks) are loaded once, coalesced, and kept in
+//      shared memory as saturated BYTES (17-word pitch per block: conflict free for the per-thread
+//      reads; the DC values separately as int16); the loading thread also records which of its
+//      eight coefficients are non-zero, so every block gets its 64-bit non-zero mask.  A byte at
+//      either end of its range sends the walk to the int16 in global memory (L2);
 //   2. every thread takes one block and walks ONLY the set bits of the mask (symbols as in
 //      b2j_entropy.cuh: gateware run-length rules, Annex-K codes), packing the block's bits
 //      MSB-first into a thread-private column of shared memory and counting them;
@@ -27,15 +28,21 @@ namespace b2j {
 constexpr int kChunk = 128;                       // blocks per CTA == threads per CTA
 constexpr int kLookahead = 8;                     // >= 31 bits / (4 bits per smallest block)
 constexpr int kCols = kChunk + kLookahead;        // blocks held in shared memory
-constexpr int kPitch = 33;                        // words per block in shared memory (32 + 1 pad)
+constexpr int kPitch = 17;                        // words per block in shared memory (64 coefficient BYTES + 1 pad)
 constexpr int kPrivWords = 55;                    // >= (1728 + 7 pad bits) / 32 + 1
-constexpr int kCap = 8;                           // private words kept in shared memory (256 bits); the rest of a
+#ifndef B2J_ENT_CAP
+#define B2J_ENT_CAP 5
+#endif
+constexpr int kCap = B2J_ENT_CAP;                 // private words kept in shared memory (160 bits); the rest of a
                                                   // (rare) larger block goes to an L2-resident scratch column
 constexpr int kOvfWords = kPrivWords - kCap;
 constexpr int kMaxSlots = 2048;                   // persistent CTAs that may own a scratch slot
 constexpr unsigned long long kFlagA = 1ull << 62, kFlagP = 2ull << 62, kValMask = (1ull << 62) - 1;
 constexpr int kSpinLimit = 1 << 22;
-constexpr int kFusedSmem = (kCols * kPitch + kCap * kCols + kCols + kCols * 2 + 32 + 512 + 16) * 4;
+#ifndef B2J_ENT_SMEM_PAD
+#define B2J_ENT_SMEM_PAD 0
+#endif
+constexpr int kFusedSmem = (kCols * kPitch + kCap * kCols + kCols + kCols * 2 + kCols / 2 + 32 + 512 + 16) * 4 + B2J_ENT_SMEM_PAD;
 
 struct FusedEntropyParams {
     const int16_t *coefs;
@@ -99,10 +106,11 @@ struct PrivSink {
 };
 
 // Sparse walk of one block: only the non-zero AC positions (set bits of the mask) are visited.
-// blk: the block's 32 words (two coefficients per word) in shared memory.  With PARTIAL the walk
-// stops once 32 bits are out (lookahead blocks only have to complete the previous word).
+// blk: the block's 64 coefficients as saturated bytes in shared memory; a byte at either end of the range (+127 / -128)
+// stands for "read the int16 from the coefficient array" (g16: the block in global memory; rare at any quality).
+// With PARTIAL the walk stops once 32 bits are out (lookahead blocks only have to complete the previous word).
 template <bool EAGER, bool PARTIAL>
-__device__ __forceinline__ void encode_block(uint32_t mlo, uint32_t mhi, int diff, const uint32_t *blk,
+__device__ __forceinline__ void encode_block(uint32_t mlo, uint32_t mhi, int diff, const uint32_t *blk, const int16_t *__restrict__ g16,
                                              const uint32_t *__restrict__ lut_dc, const uint32_t *__restrict__ lut_ac,
                                              PrivSink &sink)
 {
@@ -113,7 +121,7 @@ __device__ __forceinline__ void encode_block(uint32_t mlo, uint32_t mhi, int dif
         sink.put(((e & 0xFFFFu) << s) | extra, (int)(e >> 16) + s);
     }
     const uint32_t zrl = lut_ac[0xF0], eob = lut_ac[0x00];
-    const int16_t *c16 = reinterpret_cast<const int16_t *>(blk);
+    const int8_t *c8 = reinterpret_cast<const int8_t *>(blk);
     int prev = 0;
     uint32_t m = mlo & ~1u;                                         // position 0 is the DC
     int base = 0;
@@ -124,7 +132,8 @@ __device__ __forceinline__ void encode_block(uint32_t mlo, uint32_t mhi, int dif
             if (PARTIAL && sink.k > 0) return;
             const int z = base + __ffs((int)m) - 1;
             m &= m - 1u;
-            const int v = (int)c16[z];
+            int v = (int)c8[z];
+            if ((unsigned)(v + 127) >= 254u) v = (int)__ldg(g16 + z);          // saturated byte: the real value
             const int run = z - prev - 1;
             prev = z;
             if (run >= 16) {                                        // ZRLs in front of a non-zero: same for both policies
@@ -154,11 +163,12 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
                                                           const __grid_constant__ LutParam L)
 {
     extern __shared__ __align__(16) uint32_t fsm[];
-    uint32_t *s_coef = fsm;                                  // [kCols][kPitch]
+    uint32_t *s_coef = fsm;                                  // [kCols][kPitch]: coefficients as saturated bytes
     uint32_t *s_priv = s_coef + kCols * kPitch;              // [kCap][kCols]
     uint32_t *s_nbits = s_priv + kCap * kCols;               // [kCols]
     uint32_t *s_mask = s_nbits + kCols;                      // [kCols][2]: eight mask bytes per block
-    uint32_t *s_dc = s_mask + kCols * 2;                     // [2][16]
+    int16_t *s_dc16 = reinterpret_cast<int16_t *>(s_mask + kCols * 2);   // [kCols]: the DC coefficients, unsaturated
+    uint32_t *s_dc = s_mask + kCols * 2 + kCols / 2;         // [2][16]
     uint32_t *s_ac = s_dc + 32;                              // [2][256]
     uint32_t *s_misc = s_ac + 512;                           // warp sums [4], ticket, prefix lo/hi
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -199,28 +209,56 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
         const uint4 *src = reinterpret_cast<const uint4 *>(fc + b0 * 64);
         uint8_t *mask8 = reinterpret_cast<uint8_t *>(s_mask);
         const int npieces = nall * 8;
-        for (int i = tid; i < npieces; i += kChunk) {
-            const int b = i >> 3, c = i & 7;
-            const uint4 q = __ldg(src + i);
-            uint32_t *d = s_coef + b * kPitch + c * 4;
-            d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
-            uint32_t m = 0u;
-            if (q.x & 0xFFFFu) m |= 1u;
-            if (q.x >> 16) m |= 2u;
-            if (q.y & 0xFFFFu) m |= 4u;
-            if (q.y >> 16) m |= 8u;
-            if (q.z & 0xFFFFu) m |= 16u;
-            if (q.z >> 16) m |= 32u;
-            if (q.w & 0xFFFFu) m |= 64u;
-            if (q.w >> 16) m |= 128u;
-            mask8[b * 8 + c] = (uint8_t)m;
+#ifndef B2J_ENT_LOAD_BATCH
+#define B2J_ENT_LOAD_BATCH 3
+#endif
+        // the loads of a batch are issued together: the phase is bound by memory latency (9 dependent round trips
+        // per chunk otherwise)
+        for (int i0 = tid; i0 < npieces; i0 += B2J_ENT_LOAD_BATCH * kChunk) {
+            uint4 qb[B2J_ENT_LOAD_BATCH];
+#pragma unroll
+            for (int j = 0; j < B2J_ENT_LOAD_BATCH; j++)
+                if (i0 + j * kChunk < npieces) qb[j] = __ldg(src + i0 + j * kChunk);
+#pragma unroll
+            for (int j = 0; j < B2J_ENT_LOAD_BATCH; j++) {
+                const int i = i0 + j * kChunk;
+                if (i >= npieces) break;
+                const int b = i >> 3, c = i & 7;
+                const uint4 q = qb[j];
+                // shared memory holds bytes: both halves of a word clamped to -128..127 (packed 16-bit min / max), the low
+                // bytes of the four words gathered by two permutes.  Halving the staging area is what lets 13 instead of 8
+                // CTAs share an SM, and the kernel's speed follows its occupancy (profiles/r02/experiments.txt)
+                uint32_t t0, t1, t2, t3;
+                asm("min.s16x2 %0, %1, %2;" : "=r"(t0) : "r"(q.x), "r"(0x007F007Fu));
+                asm("min.s16x2 %0, %1, %2;" : "=r"(t1) : "r"(q.y), "r"(0x007F007Fu));
+                asm("min.s16x2 %0, %1, %2;" : "=r"(t2) : "r"(q.z), "r"(0x007F007Fu));
+                asm("min.s16x2 %0, %1, %2;" : "=r"(t3) : "r"(q.w), "r"(0x007F007Fu));
+                asm("max.s16x2 %0, %1, %2;" : "=r"(t0) : "r"(t0), "r"(0xFF80FF80u));
+                asm("max.s16x2 %0, %1, %2;" : "=r"(t1) : "r"(t1), "r"(0xFF80FF80u));
+                asm("max.s16x2 %0, %1, %2;" : "=r"(t2) : "r"(t2), "r"(0xFF80FF80u));
+                asm("max.s16x2 %0, %1, %2;" : "=r"(t3) : "r"(t3), "r"(0xFF80FF80u));
+                uint32_t *d = s_coef + b * kPitch + c * 2;
+                d[0] = __byte_perm(t0, t1, 0x6420);
+                d[1] = __byte_perm(t2, t3, 0x6420);
+                if (c == 0) s_dc16[b] = (int16_t)(q.x & 0xFFFFu);
+                // non-zero flags of the eight halves: min(half, 1) per half (one packed instruction per word), the four
+                // words interleaved by multiply-adds: low halves at bits 0, 2, 4, 6, high halves at bits 16, 18, 20, 22
+                uint32_t n0, n1, n2, n3;
+                asm("min.u16x2 %0, %1, %2;" : "=r"(n0) : "r"(q.x), "r"(0x00010001u));
+                asm("min.u16x2 %0, %1, %2;" : "=r"(n1) : "r"(q.y), "r"(0x00010001u));
+                asm("min.u16x2 %0, %1, %2;" : "=r"(n2) : "r"(q.z), "r"(0x00010001u));
+                asm("min.u16x2 %0, %1, %2;" : "=r"(n3) : "r"(q.w), "r"(0x00010001u));
+                const uint32_t mm = n0 + 4u * n1 + 16u * n2 + 64u * n3;
+                const uint32_t m = (mm | (mm >> 15)) & 0xFFu;
+                mask8[b * 8 + c] = (uint8_t)m;
+            }
         }
     }
     __syncthreads();
 
     // ---- 2. one walk per block: private packed bits + bit count
     auto dc_of = [&](long long b) -> int {          // DC of block b of this frame (b < bl)
-        if (b >= b0) return (int)(int16_t)(s_coef[(int)(b - b0) * kPitch] & 0xFFFFu);
+        if (b >= b0) return (int)s_dc16[(int)(b - b0)];
         return b >= 0 ? (int)fc[b * 64] : 0;
     };
     auto prev_index = [&](long long b) -> long long {
@@ -235,8 +273,8 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
         const long long b = b0 + tid;
         const uint32_t *blk = s_coef + tid * kPitch;
         const int chroma = (int)(b % e.bpm) >= e.hv;
-        const int diff = (int)(int16_t)(blk[0] & 0xFFFFu) - dc_of(prev_index(b));
-        encode_block<EAGER, false>(s_mask[tid * 2], s_mask[tid * 2 + 1], diff, blk, s_dc + 16 * chroma, s_ac + 256 * chroma, sink);
+        const int diff = (int)s_dc16[tid] - dc_of(prev_index(b));
+        encode_block<EAGER, false>(s_mask[tid * 2], s_mask[tid * 2 + 1], diff, blk, fc + b * 64, s_dc + 16 * chroma, s_ac + 256 * chroma, sink);
         sink.flush();
         mybits = sink.bits();
         if (mybits > (kPrivWords - 1) * 32) {                       // only with coefficients no baseline table can code
@@ -251,10 +289,10 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
         const long long b = b0 + colidx;
         const uint32_t *blk = s_coef + colidx * kPitch;
         const int chroma = (int)(b % e.bpm) >= e.hv;
-        const int diff = (int)(int16_t)(blk[0] & 0xFFFFu) - dc_of(prev_index(b));
+        const int diff = (int)s_dc16[colidx] - dc_of(prev_index(b));
         PrivSink sk;
         sk.begin(s_priv + colidx, nullptr);
-        encode_block<EAGER, true>(s_mask[colidx * 2], s_mask[colidx * 2 + 1], diff, blk, s_dc + 16 * chroma, s_ac + 256 * chroma, sk);
+        encode_block<EAGER, true>(s_mask[colidx * 2], s_mask[colidx * 2 + 1], diff, blk, fc + b * 64, s_dc + 16 * chroma, s_ac + 256 * chroma, sk);
         sk.flush();
         s_nbits[colidx] = (uint32_t)sk.bits();                      // >= 32 when the walk was cut short
     }

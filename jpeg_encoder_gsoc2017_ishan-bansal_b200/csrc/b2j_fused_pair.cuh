@@ -324,10 +324,9 @@ k_fused_pair(const __grid_constant__ FusedParams P, const __grid_constant__ CUte
             const int grp = lane & 15;
             const int row0 = V == 2 ? 2 * (lane >> 4) + 4 * pass : 2 * (lane >> 4) + (pass & 1) + 4 * (pass >> 1);
             uint32_t sy[V][4], scb[V][4], scr[V][4];
-            uint32_t cand[V], cr_flag[V];
+            uint32_t cr_flag[V];
 #pragma unroll
             for (int v = 0; v < V; v++) {
-                cand[v] = 0xFFFFFFFFu;
                 cr_flag[v] = 0u;
                 const uint32_t *q = reinterpret_cast<const uint32_t *>(raw + (row0 + v) * SS::kRawPitch + grp * 12);
                 const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
@@ -346,26 +345,30 @@ k_fused_pair(const __grid_constant__ FusedParams P, const __grid_constant__ CUte
                 }
             }
             // luma candidates: bits 10..23 of a sum are zero, i.e. its bits 8..23 as a 16-bit number are < 4
+            uint32_t hit[V], any_hit = 0u;
 #pragma unroll
             for (int v = 0; v < V; v++) {
                 uint32_t m;
                 const uint32_t a = __byte_perm(sy[v][0], sy[v][1], 0x6521), b = __byte_perm(sy[v][2], sy[v][3], 0x6521);
                 asm("min.u16x2 %0, %1, %2;" : "=r"(m) : "r"(a), "r"(b));
-                cand[v] = ((m - 0x00040004u) & ~m & 0x80008000u) ? 0u : 1u;       // some half < 4
+                hit[v] = ((m - 0x00040004u) & ~m & 0x80008000u) | cr_flag[v];      // some half < 4, or a Cr class
+                any_hit |= hit[v];
             }
+            if (any_hit) {
+                // some pixel of the item is a candidate (every grey pixel is): patch the sums of its row so that the top
+                // byte is the model's value.  Rare in photographic content.
 #pragma unroll
-            for (int v = 0; v < V; v++) {
-                if (cand[v] == 0u || cr_flag[v] != 0u) {
-                    // some pixel of this row of the item is a candidate (every grey pixel is): patch the sums so that
-                    // the top byte is the model's value.  Rare in photographic content.
-                    const uint8_t *q = raw + (row0 + v) * SS::kRawPitch + grp * 12;
+                for (int v = 0; v < V; v++) {
+                    if (hit[v]) {
+                        const uint8_t *q = raw + (row0 + v) * SS::kRawPitch + grp * 12;
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        if ((sy[v][i] & B2J_CONST_EXC_MASK) == 0u) {
-                            const uint32_t rg = q[3 * i] * 256u + q[3 * i + 1];
-                            sy[v][i] -= ((s_yx[rg >> 5] >> (rg & 31u)) & 1u) << 24;
+                        for (int i = 0; i < 4; i++) {
+                            if ((sy[v][i] & B2J_CONST_EXC_MASK) == 0u) {
+                                const uint32_t rg = q[3 * i] * 256u + q[3 * i + 1];
+                                sy[v][i] -= ((s_yx[rg >> 5] >> (rg & 31u)) & 1u) << 24;
+                            }
+                            if ((scr[v][i] & B2J_CONST_EXC_MASK) == 0u) scr[v][i] -= cr_exception(q[3 * i], q[3 * i + 1]) << 24;
                         }
-                        if ((scr[v][i] & B2J_CONST_EXC_MASK) == 0u) scr[v][i] -= cr_exception(q[3 * i], q[3 * i + 1]) << 24;
                     }
                 }
             }
@@ -427,7 +430,11 @@ k_fused_pair(const __grid_constant__ FusedParams P, const __grid_constant__ CUte
             const int nm = min(SS::kMcus, P.mcus_x - mcu0);                          // MCUs of this region inside the frame
             int16_t *dst0 = P.coefs + (((long long)cur_frame * P.mcus_y + cur_my) * P.mcus_x + mcu0) * (BPM * 64) + ochunk * 8;
             float4 kq[8];
+#ifdef B2J_PAIR_ROLL
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
             for (int r = 0; r < SS::kRounds; r++) {
                 // blocks of the round: pair p = (A, B); source rows; MCU and block index of A and B of pair `oblk`
                 const uint8_t *srcA, *srcB;

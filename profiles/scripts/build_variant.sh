@@ -13,5 +13,5 @@ for f in b2j_common b2j_stages b2j_fused b2j_entropy b2j_entropy_fused b2j_encod
 done
 wait
 nvcc $ARCH -shared -o $OUT/libb2j_$NAME.so $TMP/*.o -lcudart
-grep -A2 "k_fused_pairILi2ELi2E" $TMP/b2j_fused.log | grep -E "registers|spill" | tr '\n' ' '; echo " -> libb2j_$NAME.so"
+grep -A2 "k_fused_pairILi2ELi2E\|k_entropy_fusedILb1ELb0" $TMP/b2j_fused.log $TMP/b2j_entropy_fused.log | grep -E "registers|spill" | tr '\n' ' '; echo " -> libb2j_$NAME.so"
 rm -rf $TMP
