@@ -106,7 +106,8 @@ typedef struct b2j_geometry {
     int32_t blocks_per_mcu;       /* h*v + 2 */
     int32_t padded_width, padded_height;
     int64_t blocks_per_frame;     /* mcus_x*mcus_y*blocks_per_mcu */
-    int32_t header_bytes;         /* SOI..SOS length written in front of the scan */
+    int32_t header_bytes;         /* SOI..SOS length written in front of the scan: 623; an encode with a restart interval
+                                   * adds a 6-byte DRI segment (629), which this field does not include */
     int32_t reserved;
 } b2j_geometry;
 
@@ -188,7 +189,10 @@ int b2j_zigzag(const int16_t *in, int16_t *out, int64_t n_blocks, void *stream);
 
 /* replaces: RunLength, litejpeg/core/rle/rlecore.py:30-146.  in: n_blocks x 64
  * zig-zag ordered blocks of ONE component in scan order; prev_dc seeds the DC
- * predictor.  words: n_blocks x 64 slots, amp[0:12] run[12:16] valid[16]. */
+ * predictor.  words: n_blocks x 64 slots, amp[0:12] run[12:16] valid[16].
+ * The 4-bit zero counter starts from 0 in every block (the gateware register of
+ * rlecore.py:84-132 persists across blocks and after an EOB; one block at a time,
+ * which is all the reference bench drives, the two agree: oracle/gateware.py). */
 int b2j_run_length(const int16_t *in, uint32_t *words, int64_t n_blocks, int32_t prev_dc,
                    void *stream);
 
@@ -235,8 +239,8 @@ int b2j_scan(const int32_t *bits, const b2j_image_desc *desc, uint32_t *offsets,
  * header sketch :189-200; [ext] Annex-K Huffman codes at the scanned offsets,
  * MSB-first packing, 1-padding, 0xFF00 stuffing, JFIF header and EOI.
  * out: n_frames slots of out_cap bytes; sizes[f] = bytes of frame f, or minus
- * the bytes needed when out_cap is too small (then the call returns
- * B2J_E_CAPACITY after a stream synchronise only if check_sizes_host != 0). */
+ * the bytes needed when out_cap is too small (the call is asynchronous and returns
+ * B2J_OK either way: read sizes[]). */
 size_t b2j_bitpack_workspace_bytes(const b2j_image_desc *desc, int64_t out_cap);
 int b2j_bitpack(const int16_t *coefs, const uint32_t *offsets, const int64_t *total_bits,
                 const b2j_image_desc *desc, const uint8_t qy_host[64], const uint8_t qc_host[64],

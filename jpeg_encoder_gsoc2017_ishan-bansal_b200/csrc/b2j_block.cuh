@@ -1,5 +1,5 @@
-// The per-block pipeline shared by the fused kernel (b2j_fused.cu) and the split variant
-// (b2j_split.cu): 8x8 samples -> DCT -> quantise -> zig-zag, entirely in registers.
+// The per-block pipeline of the one-thread-per-block kernels of b2j_fused.cu (simple and tiled variants):
+// 8x8 samples -> DCT -> quantise -> zig-zag, entirely in registers.
 #pragma once
 #include "b2j_common.cuh"
 #include "b2j_math.cuh"

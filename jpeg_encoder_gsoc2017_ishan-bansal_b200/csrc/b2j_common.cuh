@@ -75,7 +75,7 @@ static const int kHeaderMax = 640;     // + DRI (6 bytes) when a restart interva
 
 // Quantisation multipliers for the fused kernel: q = (|c| * mul + 2^19) >> 20
 // reproduces round-half-away(|c| / d) for every |c| <= 1024, d in 1..255
-// (checked exhaustively in tests/test_host_math.py through csrc/host_check).
+// (checked exhaustively, every |c| <= 1024 and d in 1..255, in tests/test_kernel_identities.py).
 struct QuantMul {
     uint32_t mul[2][64];          // [luma|chroma][natural index]
 };

@@ -438,7 +438,9 @@ static FusedWs fused_ws(const Geo &g, const SegPlan &sp)
     w.total_bits = w.zero_bytes;
     w.unstuffed = up(w.total_bits + nvf * sizeof(int64_t));
     w.overflow = up(w.unstuffed + nvf * (size_t)sp.ucap);
-    w.total = w.overflow + (size_t)kMaxSlots * kOvfWords * kCols * sizeof(uint32_t);
+    // one scratch slot per persistent CTA: never more CTAs than chunks (a small frame needs kilobytes, not 56 MB)
+    const size_t total_chunks = nvf * (size_t)sp.chunks;
+    w.total = w.overflow + (total_chunks < (size_t)kMaxSlots ? total_chunks : (size_t)kMaxSlots) * kOvfWords * kCols * sizeof(uint32_t);
     return w;
 }
 

@@ -42,16 +42,25 @@ def band_plan(height, subsampling, n_bands):
     return out
 
 
-def _header_end(jpg):
-    """Offset of the first scan byte: walks the marker segments up to and including SOS."""
+def _segments(jpg):
+    """(marker, offset of the 0xFF, offset past the segment) of every marker segment up to and including SOS."""
     pos = 2
     while True:
         if jpg[pos] != 0xFF:
             raise ValueError("bad JPEG marker structure")
         marker, ln = jpg[pos + 1], (jpg[pos + 2] << 8) | jpg[pos + 3]
+        yield marker, pos, pos + 2 + ln
         pos += 2 + ln
         if marker == 0xDA:
-            return pos
+            return
+
+
+def _header_end(jpg):
+    """Offset of the first scan byte: walks the marker segments up to and including SOS."""
+    end = 0
+    for _, _, end in _segments(jpg):
+        pass
+    return end
 
 
 def assemble_bands(band_files, plan, height):
@@ -64,7 +73,8 @@ def assemble_bands(band_files, plan, height):
     first = bytes(band_files[0])
     end = _header_end(first)
     header = bytearray(first[:end])
-    sof = header.find(b"\xFF\xC0")
+    # (a search for the bytes FF C0 could land inside a quantisation table given as explicit `tables`)
+    sof = next(pos for marker, pos, _ in _segments(first) if marker == 0xC0)
     header[sof + 5] = (int(height) >> 8) & 0xFF                 # SOF0: Lf(2) P(1) Y(2) X(2)
     header[sof + 6] = int(height) & 0xFF
     parts = [bytes(header)]
