@@ -227,7 +227,7 @@ k_fused_pair(const __grid_constant__ FusedParams P, const __grid_constant__ CUte
     float4 *s_qf = reinterpret_cast<float4 *>(smem + SS::kMulBytes); // [class][x][u]
     // static: their shared addresses are compile-time constants (an immediate offset of the predicated byte load)
     __shared__ uint8_t s_crx[256];
-    __shared__ uint32_t s_yx[2048];
+    __shared__ uint32_t s_exc[4096];                                 // kYcExceptionBits
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 128; i += kPairThreads) {
         const int cls = i >> 6, x = (i >> 3) & 7, u = i & 7;
@@ -236,7 +236,7 @@ k_fused_pair(const __grid_constant__ FusedParams P, const __grid_constant__ CUte
         s_qf[i] = make_float4(P.qf.r[cls][x * 8 + u], P.qf.ha[cls][x * 8 + u], w2, w2);
     }
     for (int i = tid; i < 256; i += kPairThreads) s_crx[i] = (uint8_t)cr_exception_class((uint32_t)i);
-    for (int i = tid; i < 2048; i += kPairThreads) s_yx[i] = kYExceptionBits[i];
+    for (int i = tid; i < 4096; i += kPairThreads) s_exc[i] = kYcExceptionBits[i];
 
     uint8_t *wb = smem + SS::kTableBytes + warp * SS::kWarpBytes;
     uint8_t *raw = wb, *s_y = wb + SS::kOffY, *s_c = wb + SS::kOffC, *s_t = wb + SS::kOffT, *s_stg = wb + SS::kOffStg;
@@ -363,11 +363,13 @@ k_fused_pair(const __grid_constant__ FusedParams P, const __grid_constant__ CUte
                         const uint8_t *q = raw + (row0 + v) * SS::kRawPitch + grp * 12;
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
-                            if ((sy[v][i] & B2J_CONST_EXC_MASK) == 0u) {
+                            const bool cy = (sy[v][i] & B2J_CONST_EXC_MASK) == 0u, cc = (scr[v][i] & B2J_CONST_EXC_MASK) == 0u;
+                            if (cy || cc) {
                                 const uint32_t rg = q[3 * i] * 256u + q[3 * i + 1];
-                                sy[v][i] -= ((s_yx[rg >> 5] >> (rg & 31u)) & 1u) << 24;
+                                const uint32_t e2 = s_exc[rg >> 4] >> ((rg & 15u) * 2u);  // bit 0: Y, bit 1: Cr of the candidate
+                                if (cy) sy[v][i] -= (e2 & 1u) << 24;
+                                if (cc) scr[v][i] -= (e2 & 2u) << 23;
                             }
-                            if ((scr[v][i] & B2J_CONST_EXC_MASK) == 0u) scr[v][i] -= cr_exception(q[3 * i], q[3 * i + 1]) << 24;
                         }
                     }
                 }

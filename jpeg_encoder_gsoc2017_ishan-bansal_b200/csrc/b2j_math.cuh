@@ -68,6 +68,13 @@ __device__ __forceinline__ uint32_t csc_sum_cr(uint32_t r, uint32_t g, uint32_t 
 static __device__ const uint32_t kYExceptionBits[2048] = {
 #include "b2j_y_exceptions.inc"
 };
+// Both exception sets, two bits per (r, g): bit 0 as above, bit 1 = the Cr candidate of (r, g) (b = g, r - g even) is a real
+// exception (the 688 inputs cr_exception() lists, here generated from the model's expression).  The pair variant of K1
+// keeps this table in shared memory: one lookup patches both components of a candidate pixel, which is what every pixel of
+// a grey image is.
+static __device__ const uint32_t kYcExceptionBits[4096] = {
+#include "b2j_yc_exceptions.inc"
+};
 __device__ __forceinline__ uint32_t y_exception(uint32_t r, uint32_t g)
 {
     const uint32_t idx = r * 256u + g;

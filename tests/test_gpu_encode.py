@@ -147,6 +147,34 @@ def test_colour_exception_inputs_through_the_fused_kernel(lj, oracle_c):
             assert np.array_equal(got, exp), (sub, variant)
 
 
+def test_colour_exception_inputs_as_flat_tiles_through_every_variant(lj, oracle_c):
+    """The same inputs as 16x16 tiles of one colour each, at quality 90 (DC divisors 3: a tile whose Y or Cr is off by one
+    changes its DC coefficient): reaches the patch-up path of the stream and pair kernels, which only run for tables
+    without a divisor 1, and the grey levels (every grey pixel is a candidate of both components)."""
+    allv = np.arange(1 << 24, dtype=np.int64)
+    R, G, B = allv >> 16, (allv >> 8) & 255, allv & 255
+    ny = 299 * R + 587 * G + 114 * B
+    ncr = 5000 * R - 4187 * G - 813 * B + 1280000
+    sel = np.nonzero((ny % 1000 == 0) | ((ncr % 10000 == 0) & (G >= 150)))[0]
+    greys = np.arange(256, dtype=np.int64) * 0x010101
+    sel = np.concatenate([sel, greys])
+    tiles_x = 128
+    tiles_y = (sel.size + tiles_x - 1) // tiles_x
+    colours = np.zeros((tiles_y * tiles_x, 3), np.uint8)
+    colours[:sel.size, 0], colours[:sel.size, 1], colours[:sel.size, 2] = R[sel], G[sel], B[sel]
+    colours[sel.size:] = colours[:tiles_y * tiles_x - sel.size]
+    img = np.repeat(np.repeat(colours.reshape(tiles_y, tiles_x, 3), 16, axis=0), 16, axis=1)
+    qy, qc = J.quant_tables(90)
+    assert qy[0] == 3 and qc[0] == 3
+    dev = torch.from_numpy(img).cuda()
+    for sub in SUBS:
+        enc = lj.JpegEncoder(sub, quality=90)
+        exp = oracle_c.coefficients(img, sub, qy, qc).reshape(-1, 64)
+        for variant in ("stream", "pair", "pair_wide", "auto"):
+            got = enc.coefficients(dev, variant=variant).cpu().numpy()[0]
+            assert np.array_equal(got, exp), (sub, variant)
+
+
 def test_lena_files_decode(lj, oracle_c, golden):
     """The emitted files open in PIL / OpenCV and the oracle decoder recovers the model's coefficients."""
     from PIL import Image
