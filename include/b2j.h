@@ -89,11 +89,17 @@ extern "C" {
 #define B2J_OPT_RESTART(n) ((int)(n) << 16)
 
 /* A batch of equally sized, interleaved 8-bit RGB frames (H x W x 3, like the
- * array the model reads at test/model/enc_frame.py:7-10). */
+ * array the model reads at test/model/enc_frame.py:7-10).
+ * [ext] Other interleaved pixel layouts are read in place by K1 (no ingest pass): OR
+ * B2J_DESC_LAYOUT(layout) into `subsampling`, layout = B2J_LAYOUT_BGR, B2J_LAYOUT_RGBA or B2J_LAYOUT_BGRA
+ * (declared with b2j_ingest below; alpha is ignored, as enc_frame.py:8-10 does).  Frames are then
+ * H x W x 3 or H x W x 4 bytes and the strides count those bytes.  Results are those of the RGB
+ * frames b2j_ingest would produce.  Planar and grey sources still go through b2j_ingest. */
+#define B2J_DESC_LAYOUT(layout) ((int32_t)(layout) << 16)
 typedef struct b2j_image_desc {
     int32_t width;          /* source pixels, 1..65535 */
     int32_t height;         /* source pixels, 1..65535 */
-    int32_t subsampling;    /* B2J_SUB_* */
+    int32_t subsampling;    /* B2J_SUB_*, optionally OR-ed with B2J_DESC_LAYOUT(B2J_LAYOUT_BGR | _RGBA | _BGRA) */
     int32_t n_frames;       /* >= 1 */
     int64_t row_stride;     /* bytes between rows, >= 3*width (0 = packed) */
     int64_t frame_stride;   /* bytes between frames, >= height*row_stride (0 = packed) */

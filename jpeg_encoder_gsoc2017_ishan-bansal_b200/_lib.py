@@ -139,9 +139,12 @@ def check(code):
         raise B2JError(code, last_error())
 
 
-def make_desc(height, width, subsampling="444", n_frames=1, row_stride=0, frame_stride=0):
+def make_desc(height, width, subsampling="444", n_frames=1, row_stride=0, frame_stride=0, layout="rgb"):
+    """b2j_image_desc; layout "bgr" | "rgba" | "bgra" is OR-ed into the subsampling word (B2J_DESC_LAYOUT)."""
     sub = SUB[str(subsampling)] if str(subsampling) in SUB else int(subsampling)
-    return ImageDesc(int(width), int(height), sub, int(n_frames), int(row_stride), int(frame_stride))
+    if layout not in ("rgb", "bgr", "rgba", "bgra"):
+        raise ValueError("the encode path reads rgb, bgr, rgba or bgra frames in place; use to_rgb() for other layouts")
+    return ImageDesc(int(width), int(height), sub | (LAYOUT[layout] << 16), int(n_frames), int(row_stride), int(frame_stride))
 
 
 def geometry(desc):

@@ -99,21 +99,26 @@ int make_geo(const b2j_image_desc *d, Geo *g)
     B2J_REQUIRE(d->width >= 1 && d->width <= 65535 && d->height >= 1 && d->height <= 65535, B2J_E_SHAPE,
                 "image side out of range 1..65535: %d x %d", d->width, d->height);
     B2J_REQUIRE(d->n_frames >= 1, B2J_E_ARG, "n_frames must be >= 1");
-    switch (d->subsampling) {
+    g->layout = (d->subsampling >> 16) & 0x7FFF;
+    B2J_REQUIRE(g->layout == B2J_LAYOUT_RGB || g->layout == B2J_LAYOUT_BGR || g->layout == B2J_LAYOUT_RGBA || g->layout == B2J_LAYOUT_BGRA,
+                B2J_E_ARG, "descriptor layout must be RGB, BGR, RGBA or BGRA (got %d)", g->layout);
+    g->bpp = (g->layout == B2J_LAYOUT_RGBA || g->layout == B2J_LAYOUT_BGRA) ? 4 : 3;
+    switch (d->subsampling & 0xFFFF) {
     case B2J_SUB_444: g->h = 1; g->v = 1; break;
     case B2J_SUB_422: g->h = 2; g->v = 1; break;
     case B2J_SUB_420: g->h = 2; g->v = 2; break;
-    default: B2J_REQUIRE(false, B2J_E_ARG, "subsampling must be 444, 422 or 420 (got %d)", d->subsampling);
+    default: B2J_REQUIRE(false, B2J_E_ARG, "subsampling must be 444, 422 or 420 (got %d)", d->subsampling & 0xFFFF);
     }
     g->width = d->width; g->height = d->height; g->n_frames = d->n_frames;
     g->mcu_w = 8 * g->h; g->mcu_h = 8 * g->v;
     g->mcus_x = (d->width + g->mcu_w - 1) / g->mcu_w;
     g->mcus_y = (d->height + g->mcu_h - 1) / g->mcu_h;
     g->bpm = g->h * g->v + 2;
-    g->row_stride = d->row_stride ? d->row_stride : 3LL * d->width;
+    const long long row_bytes = (long long)g->bpp * d->width;
+    g->row_stride = d->row_stride ? d->row_stride : row_bytes;
     g->frame_stride = d->frame_stride ? d->frame_stride : g->row_stride * d->height;
-    B2J_REQUIRE(g->row_stride >= 3LL * d->width, B2J_E_ARG, "row_stride smaller than 3*width");
-    B2J_REQUIRE(g->frame_stride >= g->row_stride * (long long)(d->height - 1) + 3LL * d->width, B2J_E_ARG,
+    B2J_REQUIRE(g->row_stride >= row_bytes, B2J_E_ARG, "row_stride smaller than %d*width", g->bpp);
+    B2J_REQUIRE(g->frame_stride >= g->row_stride * (long long)(d->height - 1) + row_bytes, B2J_E_ARG,
                 "frame_stride smaller than one frame");
     g->blocks_per_frame = (long long)g->mcus_x * g->mcus_y * g->bpm;
     // bit offsets inside one frame are 32-bit: worst case 64 * 27 bits per block

@@ -64,6 +64,7 @@ struct Geo {
     int mcus_x, mcus_y;
     int bpm;                      // blocks per MCU
     int n_frames;
+    int layout, bpp;              // B2J_LAYOUT_RGB | BGR | RGBA | BGRA of the source frames; bytes per pixel
     long long row_stride, frame_stride;   // bytes
     long long blocks_per_frame;
 };

@@ -160,7 +160,7 @@ extern "C" int b2j_encoder_create(b2j_encoder **enc, const b2j_image_desc *desc,
     memset(e, 0, sizeof *e);
     if (cudaGetDevice(&e->device) != cudaSuccess) { delete e; return cuda_fail(cudaGetLastError(), "b2j_encoder_create"); }
     e->desc = d; e->quality = quality; e->zrl = zrl; e->out_cap = out_cap;
-    e->frame_bytes = (size_t)g.height * (size_t)g.width * 3;
+    e->frame_bytes = (size_t)g.height * (size_t)g.width * (size_t)g.bpp;
     e->ws_bytes = b2j_encode_workspace_bytes_opts(&d, out_cap, zrl);
     if (!e->ws_bytes) { encoder_free(e); return B2J_E_CAPACITY; }
     for (int s = 0; s < b2j_encoder::kSlots; s++) {

@@ -37,6 +37,7 @@ struct FusedParams {
     int mcus_x, mcus_y;
     int n_frames;
     int aligned;                  // rows may use bulk-async copies
+    int bpp, ro;                  // [ext] source layout: bytes per pixel, byte of r in a pixel (b at 2 - ro); pair and simple variants
     QuantMul qm;
     QuantF32 qf;                  // pair variant only
 };
@@ -67,8 +68,8 @@ __global__ void __launch_bounds__(128) k_fused_simple(const __grid_constant__ Fu
             if (comp == 0) {
                 int yy = my * 8 * V + (k / H) * 8 + i, xx = mx * 8 * H + (k % H) * 8 + j;
                 yy = min(yy, P.height - 1); xx = min(xx, P.width - 1);          // edge replication
-                const uint8_t *q = img + (long long)yy * P.row_stride + 3LL * xx;
-                s = rgb2ycbcr_px(q[0], q[1], q[2]) & 0xFFu;
+                const uint8_t *q = img + (long long)yy * P.row_stride + (long long)P.bpp * xx;
+                s = rgb2ycbcr_px(q[P.ro], q[1], q[2 - P.ro]) & 0xFFu;
             } else {
                 int acc_v = 0;
                 for (int dy = 0; dy < V; dy++) {
@@ -76,8 +77,8 @@ __global__ void __launch_bounds__(128) k_fused_simple(const __grid_constant__ Fu
                     for (int dx = 0; dx < H; dx++) {
                         int yy = min(my * 8 * V + i * V + dy, P.height - 1);
                         int xx = min(mx * 8 * H + j * H + dx, P.width - 1);
-                        const uint8_t *q = img + (long long)yy * P.row_stride + 3LL * xx;
-                        acc_h += (int)((rgb2ycbcr_px(q[0], q[1], q[2]) >> (8 * comp)) & 0xFFu);
+                        const uint8_t *q = img + (long long)yy * P.row_stride + (long long)P.bpp * xx;
+                        acc_h += (int)((rgb2ycbcr_px(q[P.ro], q[1], q[2 - P.ro]) >> (8 * comp)) & 0xFFu);
                     }
                     acc_v += H == 2 ? acc_h >> 1 : acc_h;                        // crs.py:39-54 pair mean
                 }
@@ -417,7 +418,7 @@ static bool make_frame_map(const FusedParams &P, int box_bytes, int box_rows, CU
     }();
     memset(map, 0, sizeof *map);
     if (!encode || !P.aligned || P.row_stride >= (1LL << 40) || P.frame_stride >= (1LL << 40)) return false;
-    const cuuint64_t dims[3] = {(cuuint64_t)P.width * 3, (cuuint64_t)P.height, (cuuint64_t)P.n_frames};
+    const cuuint64_t dims[3] = {(cuuint64_t)P.width * P.bpp, (cuuint64_t)P.height, (cuuint64_t)P.n_frames};
     const cuuint64_t strides[2] = {(cuuint64_t)P.row_stride, (cuuint64_t)P.frame_stride};
     const cuuint32_t box[3] = {(cuuint32_t)box_bytes, (cuuint32_t)box_rows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
@@ -426,51 +427,67 @@ static bool make_frame_map(const FusedParams &P, int box_bytes, int box_rows, CU
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// The pair variant for one source layout.  Returns 1 when the launch was left to the stream variant (a single frame, or more
+// than 2^32 regions), 0 after a launch, < 0 on error.
+template <int H, int V, int LAYOUT>
+static int launch_pair(FusedParams &P, const Geo &g, cudaStream_t st, bool auto_pick)
+{
+    constexpr int BPP = (LAYOUT == B2J_LAYOUT_RGBA || LAYOUT == B2J_LAYOUT_BGRA) ? 4 : 3;
+    using SS = PairShape<H, V, BPP>;
+    const int regions_x = (g.mcus_x * 8 * H + SS::kRegW - 1) / SS::kRegW;
+    const long long n_regions = (long long)regions_x * g.mcus_y * g.n_frames;
+    if (n_regions >= 0xFFF00000LL) return 1;
+    static LaunchInfo cache[kMaxDevices];
+    LaunchInfo li;
+    int rc = launch_info(k_fused_pair<H, V, LAYOUT>, kPairThreads, SS::kSmem, cache, &li);
+    if (rc) return rc;
+    // a few regions per warp only (a single frame): the stream variant's 32-pixel regions spread wider
+    // (one 1080p frame: 10.7 us against 12.6 us)
+    if (auto_pick && LAYOUT == B2J_LAYOUT_RGB && n_regions < 3 * (long long)li.per_sm * li.sms * kPairWarps) return 1;
+    // regions per work item: the run length (<= kPairRun) with the smallest load of the busiest warp, an item
+    // counted as its regions plus a fifth of a region for its own arithmetic
+    const long long slots = (long long)li.per_sm * li.sms * kPairWarps;
+    int run = 1;
+    long long best = -1;
+    for (int r = 1; r <= kPairRun && r <= regions_x; r++) {
+        const long long items = n_regions / regions_x * ((regions_x + r - 1) / r);
+        const long long cost = (items + slots - 1) / slots * (5 * r + 1);
+        if (best < 0 || cost < best) { best = cost; run = r; }
+    }
+    const long long n_items = n_regions / regions_x * ((regions_x + run - 1) / run);
+    const long long ctas_needed = (n_items + kPairWarps - 1) / kPairWarps;
+    const long long grid = ctas_needed < (long long)li.per_sm * li.sms ? ctas_needed : (long long)li.per_sm * li.sms;
+    CUtensorMap map;
+    if (!make_frame_map(P, SS::kRawPitch, SS::kRows, &map)) P.aligned = 0;
+    k_fused_pair<H, V, LAYOUT><<<(unsigned)grid, kPairThreads, SS::kSmem, st>>>(P, map, (unsigned)n_regions, regions_x, run);
+    B2J_LAUNCH_CHECK("k_fused_pair");
+    return 0;
+}
+
 template <int H, int V, bool FIXED>
 static int launch_fused(const FusedParams &P0, const Geo &g, int variant, cudaStream_t st, bool auto_pick = false)
 {
     FusedParams P = P0;
-    if (variant == B2J_FUSED_SIMPLE) {
+    auto simple = [&]() -> int {
         const long long nblk = (long long)g.n_frames * g.blocks_per_frame;
         k_fused_simple<H, V, FIXED><<<(unsigned)((nblk + 127) / 128), 128, 0, st>>>(P);
         B2J_LAUNCH_CHECK("k_fused_simple");
         return B2J_OK;
-    }
+    };
+    if (variant == B2J_FUSED_SIMPLE) return simple();
     if (variant == B2J_FUSED_PAIR && !FIXED) {
-        using SS = PairShape<H, V>;
-        const int regions_x = (g.mcus_x * 8 * H + SS::kRegW - 1) / SS::kRegW;
-        const long long n_regions = (long long)regions_x * g.mcus_y * g.n_frames;
-        if (n_regions < 0xFFF00000LL) {
-            static LaunchInfo cache[kMaxDevices];
-            LaunchInfo li;
-            int rc = launch_info(k_fused_pair<H, V>, kPairThreads, SS::kSmem, cache, &li);
-            if (rc) return rc;
-            // a few regions per warp only (a single frame): the stream variant's 32-pixel regions spread wider
-            // (one 1080p frame: 10.7 us against 12.6 us)
-            if (auto_pick && n_regions < 3 * (long long)li.per_sm * li.sms * kPairWarps) goto stream_variant;
-            // regions per work item: the run length (<= kPairRun) with the smallest load of the busiest warp, an item
-            // counted as its regions plus a fifth of a region for its own arithmetic
-            const long long slots = (long long)li.per_sm * li.sms * kPairWarps;
-            int run = 1;
-            long long best = -1;
-            for (int r = 1; r <= kPairRun && r <= regions_x; r++) {
-                const long long items = n_regions / regions_x * ((regions_x + r - 1) / r);
-                const long long cost = (items + slots - 1) / slots * (5 * r + 1);
-                if (best < 0 || cost < best) { best = cost; run = r; }
-            }
-            const long long n_items = n_regions / regions_x * ((regions_x + run - 1) / run);
-            const long long ctas_needed = (n_items + kPairWarps - 1) / kPairWarps;
-            const long long grid = ctas_needed < (long long)li.per_sm * li.sms ? ctas_needed : (long long)li.per_sm * li.sms;
-            CUtensorMap map;
-            if (!make_frame_map(P, SS::kRawPitch, SS::kRows, &map)) P.aligned = 0;
-            k_fused_pair<H, V><<<(unsigned)grid, kPairThreads, SS::kSmem, st>>>(P, map, (unsigned)n_regions, regions_x, run);
-            B2J_LAUNCH_CHECK("k_fused_pair");
-            return B2J_OK;
+        int rc;
+        switch (g.layout) {
+        case B2J_LAYOUT_BGR: rc = launch_pair<H, V, B2J_LAYOUT_BGR>(P, g, st, auto_pick); break;
+        case B2J_LAYOUT_RGBA: rc = launch_pair<H, V, B2J_LAYOUT_RGBA>(P, g, st, auto_pick); break;
+        case B2J_LAYOUT_BGRA: rc = launch_pair<H, V, B2J_LAYOUT_BGRA>(P, g, st, auto_pick); break;
+        default: rc = launch_pair<H, V, B2J_LAYOUT_RGB>(P, g, st, auto_pick); break;
         }
-    stream_variant:
-        variant = B2J_FUSED_STREAM;
+        if (rc <= 0) return rc;
+        variant = g.layout == B2J_LAYOUT_RGB ? B2J_FUSED_STREAM : B2J_FUSED_SIMPLE;
     }
-    if (variant == B2J_FUSED_PAIR) variant = B2J_FUSED_STREAM;      // (the gateware DCT has no single-precision path)
+    if (variant == B2J_FUSED_PAIR) variant = g.layout == B2J_LAYOUT_RGB ? B2J_FUSED_STREAM : B2J_FUSED_SIMPLE;   // (gateware DCT)
+    if (variant == B2J_FUSED_SIMPLE) return simple();
     if (variant == B2J_FUSED_STREAM) {
         using SS = StreamShape<H, V>;
         const int regions_x = (g.mcus_x * 8 * H + SS::kRegW - 1) / SS::kRegW;
@@ -531,6 +548,8 @@ extern "C" int b2j_fused_block(const uint8_t *rgb, const b2j_image_desc *desc, c
     P.row_stride = g.row_stride; P.frame_stride = g.frame_stride;
     P.width = g.width; P.height = g.height; P.mcus_x = g.mcus_x; P.mcus_y = g.mcus_y; P.n_frames = g.n_frames;
     P.aligned = (((uintptr_t)rgb & 15) == 0 && (g.row_stride & 15) == 0 && (g.frame_stride & 15) == 0) ? 1 : 0;
+    P.bpp = g.bpp;
+    P.ro = (g.layout == B2J_LAYOUT_BGR || g.layout == B2J_LAYOUT_BGRA) ? 2 : 0;
     make_quant_mul(qy_host, qc_host, &P.qm);
     const bool fast_ok = make_quant_f32(qy_host, qc_host, &P.qf, wide ? 0.25 : kFastPathErr);
     cudaStream_t st = as_stream(stream);
@@ -540,6 +559,13 @@ extern "C" int b2j_fused_block(const uint8_t *rgb, const b2j_image_desc *desc, c
     const bool auto_pick = variant == B2J_FUSED_AUTO;
     if (variant == B2J_FUSED_AUTO) variant = B2J_FUSED_DEFAULT;
     if (variant == B2J_FUSED_PAIR && !fast_ok) variant = B2J_FUSED_STREAM;    // a divisor 1: exact arithmetic throughout
+    if (g.layout != B2J_LAYOUT_RGB) {
+        // [ext] other source layouts are read in place by the pair variant; what that variant does not cover (gateware
+        // DCT, a divisor 1) goes to the one-thread-per-block kernel
+        B2J_REQUIRE(auto_pick || variant == B2J_FUSED_PAIR || variant == B2J_FUSED_SIMPLE, B2J_E_ARG,
+                    "b2j_fused_block: only the pair and simple variants read layouts other than RGB");
+        if (variant != B2J_FUSED_PAIR || fixed) variant = B2J_FUSED_SIMPLE;
+    }
     if (fixed) {
         if (g.h == 1) return launch_fused<1, 1, true>(P, g, variant, st);
         if (g.v == 1) return launch_fused<2, 1, true>(P, g, variant, st);

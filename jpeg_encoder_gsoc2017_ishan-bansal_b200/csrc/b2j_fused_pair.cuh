@@ -110,13 +110,14 @@ __device__ __forceinline__ void dct_1d_pair(f32x2 (&v)[8])
     v[5] = e6;
 }
 
-template <int H, int V>
+template <int H, int V, int BPP = 3>
 struct PairShape {
     static constexpr int kRegW = 64;                              // pixels per region row
     static constexpr int kRows = 8 * V;
-    static constexpr int kRowBytes = kRegW * 3;                   // 192
-    // pitches: two lanes of an item pass work on rows two apart; 56 and 24 words put them on disjoint banks
-    static constexpr int kRawPitch = 224;                         // = the box width of the tensor copy
+    static constexpr int kRowBytes = kRegW * BPP;                 // 192 (256 for the four-byte layouts)
+    // pitches: two lanes of an item pass work on rows two apart; 56 and 24 words put them on disjoint banks (four-byte
+    // pixels are read as one 16-byte piece per lane: any pitch is conflict free)
+    static constexpr int kRawPitch = BPP == 3 ? 224 : 256;        // = the box width of the tensor copy
     static constexpr int kRawBytes = kRows * kRawPitch;
     static constexpr int kYPitch = 96;
     static constexpr int kYBytes = kRows * kYPitch;
@@ -215,12 +216,15 @@ __device__ __noinline__ void pair_exact_round(const uint8_t *src, uint8_t *t_row
     stream_round<false>(src, t_row, t_col, s, mul8);
 }
 
-template <int H, int V>
+// LAYOUT: B2J_LAYOUT_RGB | BGR | RGBA | BGRA of the source frames ([ext] SURVEY 8f-4: read in place, no ingest pass).
+template <int H, int V, int LAYOUT = B2J_LAYOUT_RGB>
 __global__ void __launch_bounds__(kPairThreads, B2J_PAIR_MIN_CTAS)
 k_fused_pair(const __grid_constant__ FusedParams P, const __grid_constant__ CUtensorMap tmap, unsigned n_regions, int regions_x,
              int kRun)
 {
-    using SS = PairShape<H, V>;
+    constexpr int BPP = (LAYOUT == B2J_LAYOUT_RGBA || LAYOUT == B2J_LAYOUT_BGRA) ? 4 : 3;
+    constexpr int RO = (LAYOUT == B2J_LAYOUT_BGR || LAYOUT == B2J_LAYOUT_BGRA) ? 2 : 0, BO = 2 - RO;   // byte of r and b in a pixel
+    using SS = PairShape<H, V, BPP>;
     constexpr int BPM = H * V + 2;
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t *s_mul = reinterpret_cast<uint32_t *>(smem);            // [class][u][12]: mul[class][x * 8 + u] at x
@@ -306,9 +310,9 @@ k_fused_pair(const __grid_constant__ FusedParams P, const __grid_constant__ CUte
             const uint8_t *img = P.rgb + (long long)frame * P.frame_stride + (long long)(my * SS::kRows) * P.row_stride;
             for (int i = lane; i < SS::kRows * SS::kRowBytes; i += 32) {
                 const int row = i / SS::kRowBytes, j = i - row * SS::kRowBytes;
-                const int px = j / 3, ch = j - 3 * px;
+                const int px = j / BPP, ch = j - BPP * px;
                 const int sx = min(rx * SS::kRegW + px, P.width - 1);
-                raw[row * SS::kRawPitch + j] = img[(long long)min(row, vr - 1) * P.row_stride + 3LL * sx + ch];
+                raw[row * SS::kRawPitch + j] = img[(long long)min(row, vr - 1) * P.row_stride + (long long)BPP * sx + ch];
             }
         }
         __syncwarp();
@@ -328,13 +332,26 @@ k_fused_pair(const __grid_constant__ FusedParams P, const __grid_constant__ CUte
 #pragma unroll
             for (int v = 0; v < V; v++) {
                 cr_flag[v] = 0u;
-                const uint32_t *q = reinterpret_cast<const uint32_t *>(raw + (row0 + v) * SS::kRawPitch + grp * 12);
-                const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
                 uint32_t cr[4], cg[4], cb[4];
-                cr[0] = __byte_perm(w0, 0u, 0x4440); cg[0] = __byte_perm(w0, 0u, 0x4441); cb[0] = __byte_perm(w0, 0u, 0x4442);
-                cr[1] = __byte_perm(w0, 0u, 0x4443); cg[1] = __byte_perm(w1, 0u, 0x4440); cb[1] = __byte_perm(w1, 0u, 0x4441);
-                cr[2] = __byte_perm(w1, 0u, 0x4442); cg[2] = __byte_perm(w1, 0u, 0x4443); cb[2] = __byte_perm(w2, 0u, 0x4440);
-                cr[3] = __byte_perm(w2, 0u, 0x4441); cg[3] = __byte_perm(w2, 0u, 0x4442); cb[3] = __byte_perm(w2, 0u, 0x4443);
+                if (BPP == 3) {
+                    const uint32_t *q = reinterpret_cast<const uint32_t *>(raw + (row0 + v) * SS::kRawPitch + grp * 12);
+                    const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+                    uint32_t c0[4], c2[4];                           // first and third byte of every pixel
+                    c0[0] = __byte_perm(w0, 0u, 0x4440); cg[0] = __byte_perm(w0, 0u, 0x4441); c2[0] = __byte_perm(w0, 0u, 0x4442);
+                    c0[1] = __byte_perm(w0, 0u, 0x4443); cg[1] = __byte_perm(w1, 0u, 0x4440); c2[1] = __byte_perm(w1, 0u, 0x4441);
+                    c0[2] = __byte_perm(w1, 0u, 0x4442); cg[2] = __byte_perm(w1, 0u, 0x4443); c2[2] = __byte_perm(w2, 0u, 0x4440);
+                    c0[3] = __byte_perm(w2, 0u, 0x4441); cg[3] = __byte_perm(w2, 0u, 0x4442); c2[3] = __byte_perm(w2, 0u, 0x4443);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { cr[i] = RO == 0 ? c0[i] : c2[i]; cb[i] = RO == 0 ? c2[i] : c0[i]; }
+                } else {
+                    const uint4 q = *reinterpret_cast<const uint4 *>(raw + (row0 + v) * SS::kRawPitch + grp * 16);
+                    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        cr[i] = __byte_perm(w[i], 0u, 0x4440 + RO); cg[i] = __byte_perm(w[i], 0u, 0x4441);
+                        cb[i] = __byte_perm(w[i], 0u, 0x4440 + BO);
+                    }
+                }
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     sy[v][i] = csc_sum_y(cr[i], cg[i], cb[i]);
@@ -360,12 +377,12 @@ k_fused_pair(const __grid_constant__ FusedParams P, const __grid_constant__ CUte
 #pragma unroll
                 for (int v = 0; v < V; v++) {
                     if (hit[v]) {
-                        const uint8_t *q = raw + (row0 + v) * SS::kRawPitch + grp * 12;
+                        const uint8_t *q = raw + (row0 + v) * SS::kRawPitch + grp * (4 * BPP);
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
                             const bool cy = (sy[v][i] & B2J_CONST_EXC_MASK) == 0u, cc = (scr[v][i] & B2J_CONST_EXC_MASK) == 0u;
                             if (cy || cc) {
-                                const uint32_t rg = q[3 * i] * 256u + q[3 * i + 1];
+                                const uint32_t rg = q[BPP * i + RO] * 256u + q[BPP * i + 1];
                                 const uint32_t e2 = s_exc[rg >> 4] >> ((rg & 15u) * 2u);  // bit 0: Y, bit 1: Cr of the candidate
                                 if (cy) sy[v][i] -= (e2 & 1u) << 24;
                                 if (cc) scr[v][i] -= (e2 & 2u) << 23;

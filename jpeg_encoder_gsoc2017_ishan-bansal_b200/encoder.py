@@ -100,16 +100,22 @@ class JpegEncoder:
     arithmetic, new_dct6.py:171-396 corrected; <= 4 LSB per coefficient from the model, not parity).
     restart_interval: [ext] MCUs per restart interval (0 = none): DRI + RSTm markers, DC predictors
     restart; the intervals are independent byte-aligned streams.
+    layout: [ext] "rgb" | "bgr" | "rgba" | "bgra": the pixel layout of the frames handed to the encoder
+    (last dimension 3 or 4); K1 reads them in place, the files are those of the RGB frames.
     """
 
     def __init__(self, subsampling="444", quality=85, zrl="eager", tables=None, out_cap=None, dct="model",
-                 restart_interval=0):
+                 restart_interval=0, layout="rgb"):
         if str(subsampling) not in _lib.SUB:
             raise ValueError("subsampling must be '444', '422' or '420'")
         if zrl not in _lib.ZRL:
             raise ValueError("zrl must be 'eager' or 'standard'")
         if dct not in _lib.DCT_MODE:
             raise ValueError("dct must be 'model' (float64 model, the parity path) or 'fixed' ([ext] gateware arithmetic)")
+        if layout not in ("rgb", "bgr", "rgba", "bgra"):
+            raise ValueError("layout must be 'rgb', 'bgr', 'rgba' or 'bgra'")
+        self.layout = layout
+        self.bpp = 4 if layout in ("rgba", "bgra") else 3
         self.subsampling = str(subsampling)
         self.zrl = zrl
         self.dct = dct
@@ -133,13 +139,13 @@ class JpegEncoder:
 
     # ------------------------------------------------------------------ helpers
     def desc_for(self, rgb):
-        if rgb.dtype != torch.uint8 or rgb.dim() not in (3, 4) or rgb.shape[-1] != 3:
-            raise ValueError("rgb must be uint8 (H, W, 3) or (N, H, W, 3)")
+        if rgb.dtype != torch.uint8 or rgb.dim() not in (3, 4) or rgb.shape[-1] != self.bpp:
+            raise ValueError("%s frames must be uint8 (H, W, %d) or (N, H, W, %d)" % (self.layout, self.bpp, self.bpp))
         n = 1 if rgb.dim() == 3 else rgb.shape[0]
         if n == 0:
             raise ValueError("empty batch")
         h, w = rgb.shape[-3], rgb.shape[-2]
-        return _lib.make_desc(h, w, self.subsampling, n)
+        return _lib.make_desc(h, w, self.subsampling, n, layout=self.layout)
 
     def _cap(self, desc):
         return int(self.out_cap or _lib.lib().b2j_default_out_cap(ctypes.byref(desc)))
@@ -261,14 +267,14 @@ class JpegEncoder:
         rgb_host = rgb_host.contiguous()
         desc = self.desc_for(rgb_host)
         n = desc.n_frames
-        fpc = int(frames_per_chunk or max(1, min(n, (64 << 20) // max(1, desc.height * desc.width * 3))))
+        fpc = int(frames_per_chunk or max(1, min(n, (64 << 20) // max(1, desc.height * desc.width * self.bpp))))
         cap = self._cap(_lib.make_desc(desc.height, desc.width, self.subsampling, 1))
         key = (desc.height, desc.width, fpc, cap, torch.cuda.current_device())
         enc = self._host.get(key)
         if enc is None:
             self.close()
             handle = ctypes.c_void_p()
-            d1 = _lib.make_desc(desc.height, desc.width, self.subsampling, fpc)
+            d1 = _lib.make_desc(desc.height, desc.width, self.subsampling, fpc, layout=self.layout)
             if self.quality == 0:
                 raise ValueError("encode_host needs a quality (explicit tables are not supported on this path)")
             _lib.check(_lib.lib().b2j_encoder_create(ctypes.byref(handle), ctypes.byref(d1), self.quality, self._opts,

@@ -175,6 +175,61 @@ def test_colour_exception_inputs_as_flat_tiles_through_every_variant(lj, oracle_
             assert np.array_equal(got, exp), (sub, variant)
 
 
+@pytest.mark.parametrize("layout", ["bgr", "rgba", "bgra"])
+def test_source_layouts_are_read_in_place(lj, oracle_c, layout):
+    """[ext] SURVEY 8f-4: BGR / RGBA / BGRA frames go straight into K1 (B2J_DESC_LAYOUT): coefficients and files equal
+    those of the RGB frames, for every subsampling, ragged sizes (edge regions, unaligned rows), a strided crop, the
+    kernels that read other layouts (pair, simple; AUTO) and the host-buffer encoder."""
+    s = synth(lj)
+    rng = np.random.default_rng(3)
+
+    def convert(rgb):                                   # (N, H, W, 3) uint8 tensor -> the layout under test
+        a = rgb.numpy()
+        if layout in ("bgr", "bgra"):
+            a = a[..., ::-1]
+        if layout in ("rgba", "bgra"):
+            a = np.concatenate([a, rng.integers(0, 256, a.shape[:-1] + (1,), dtype=np.uint8)], axis=-1)
+        return torch.from_numpy(np.ascontiguousarray(a))
+
+    for sub in SUBS:
+        for (h, w) in ((64, 128), (73, 200), (160, 1000)):
+            rgb = s.batch(2, h, w, 9, "photo")
+            src = convert(rgb)
+            exp = np.stack([oracle_c.coefficients(rgb[i].numpy(), sub, *J.quant_tables(75)) for i in range(2)])
+            enc = lj.JpegEncoder(sub, quality=75, layout=layout)
+            for variant in ("auto", "pair", "simple"):
+                got = enc.coefficients(src.cuda(), variant=variant).cpu().numpy()
+                assert np.array_equal(got.reshape(exp.shape), exp), (sub, h, w, variant)
+            files = enc.encode(src.cuda())
+            ref = lj.JpegEncoder(sub, quality=75).encode(rgb.cuda())
+            assert files == ref, (sub, h, w)
+    # gateware DCT and a divisor 1 are outside the pair variant: the one-thread-per-block kernel reads the layout
+    rgb = s.batch(1, 48, 80, 10, "noise")
+    src = convert(rgb).cuda()
+    assert lj.JpegEncoder("420", quality=100, layout=layout).encode(src) == lj.JpegEncoder("420", quality=100).encode(rgb.cuda())
+    assert lj.JpegEncoder("422", quality=60, dct="fixed", layout=layout).encode(src) == \
+        lj.JpegEncoder("422", quality=60, dct="fixed").encode(rgb.cuda())
+    # host-buffer encoder: frames of the layout in, the same files out
+    rgb = s.batch(3, 96, 160, 11, "photo")
+    out, sizes = lj.JpegEncoder("420", quality=75, layout=layout).encode_host(convert(rgb))
+    ref = lj.JpegEncoder("420", quality=75).encode(rgb.cuda())
+    for i in range(3):
+        assert bytes(out[i, :int(sizes[i])].numpy()) == ref[i]
+    # a crop of a larger buffer through the strides of the descriptor
+    big = convert(s.batch(1, 128, 256, 12, "photo"))[0].cuda()
+    bpp = big.shape[-1]
+    desc = lj.make_desc(72, 104, "420", 1, row_stride=256 * bpp, frame_stride=256 * bpp * 128, layout=layout)
+    g = lj.geometry(desc)
+    qy, qc = lj.quant_tables(75)
+    coefs = torch.empty((1, g.blocks_per_frame, 64), dtype=torch.int16, device="cuda")
+    lj._lib.check(lj.lib().b2j_fused_block(big.data_ptr() + (16 * 256 + 32) * bpp, ctypes.byref(desc), lj._lib.table_arg(qy),
+                                           lj._lib.table_arg(qc), coefs.data_ptr(), 0, torch.cuda.current_stream().cuda_stream))
+    crop = big[16:88, 32:136].cpu().numpy()
+    crop = crop[..., 2::-1] if layout in ("bgr", "bgra") else crop[..., :3]
+    exp = oracle_c.coefficients(np.ascontiguousarray(crop), "420", *J.quant_tables(75))
+    assert np.array_equal(coefs.cpu().numpy()[0], exp.reshape(-1, 64))
+
+
 def test_lena_files_decode(lj, oracle_c, golden):
     """The emitted files open in PIL / OpenCV and the oracle decoder recovers the model's coefficients."""
     from PIL import Image
