@@ -277,7 +277,7 @@ int b2j_encode(const uint8_t *rgb, const b2j_image_desc *desc, int quality,
                void *workspace, size_t workspace_bytes,
                uint8_t *out, int64_t out_cap, int64_t *sizes, void *stream);
 
-/* Number of kernel launches b2j_encode issues for this geometry. */
+/* Number of kernel launches b2j_encode issues for this geometry (3; one more with restart intervals). */
 int b2j_encode_launch_count(const b2j_image_desc *desc);
 
 /* ---------------------------------------------------------------- host-buffer encoder (end-to-end)

@@ -63,7 +63,7 @@ extern "C" size_t b2j_encode_workspace_bytes(const b2j_image_desc *desc, int64_t
 extern "C" int b2j_encode_launch_count(const b2j_image_desc *desc)
 {
     (void)desc;
-    return 4;   // k_fused_tiled, k_entropy_fused, k_ff_scan, k_stuff_write (+ one small memset)
+    return 3;   // k_fused_pair (or _stream), k_entropy_fused, k_stuff_write (+ one small memset; + k_ff_scan with restart intervals)
 }
 
 extern "C" int b2j_encode(const uint8_t *rgb, const b2j_image_desc *desc, int quality, const uint8_t qy_host[64],

@@ -288,23 +288,52 @@ __global__ void __launch_bounds__(256) k_ff_scan(uint32_t *__restrict__ ffpart, 
 // has (the slot capacity is several times the typical stream: empty CTAs cost more than the copy).
 // The first segment's first CTA writes the header; the CTA that writes a segment's last chunk
 // appends the marker that follows it: RSTm between segments, EOI after the last one.
+// OWN_SCAN (frames of one segment, i.e. no restart intervals): the CTA scans the 0xFF counts of its frame's chunks itself
+// (a few hundred values) and derives the file size and the capacity verdict - no k_ff_scan launch in front; ffpart then
+// holds the raw counts and segbase is not used.
+template <bool OWN_SCAN>
 __global__ void __launch_bounds__(256) k_stuff_write(const uint8_t *__restrict__ unstuffed, const int64_t *__restrict__ total_bits,
                                                      const uint32_t *__restrict__ ffpart, const uint32_t *__restrict__ segbase,
-                                                     const int64_t *__restrict__ sizes, uint8_t *__restrict__ out, long long ucap,
+                                                     int64_t *__restrict__ sizes, uint8_t *__restrict__ out, long long ucap,
                                                      long long out_cap, int chunks, int nseg, int rst_phase,
-                                                     const __grid_constant__ HeaderParam H)
+                                                     const int *__restrict__ error_flag, const __grid_constant__ HeaderParam H)
 {
+    extern __shared__ uint32_t s_prefix[];                          // OWN_SCAN: exclusive prefix of the frame's 0xFF counts
     __shared__ uint32_t s_warp[8];
     __shared__ __align__(16) uint8_t s_out[2 * kStuffChunk + 16];
     const long long vf = blockIdx.x;
     const long long f = vf / nseg;
     const int seg = (int)(vf % nseg);
-    if (sizes[f] < 0) return;                                       // slot too small: leave it untouched
     const long long nbytes = (total_bits[vf] + 7) >> 3;
+    if (OWN_SCAN) {
+        const int nused = (int)min((long long)chunks, (nbytes + kStuffChunk - 1) / kStuffChunk);
+        unsigned long long c0 = 0;
+        for (int base = 0; base < nused; base += 256) {
+            const int i = base + threadIdx.x;
+            const uint32_t v = i < nused ? ffpart[vf * chunks + i] : 0u;
+            uint32_t tot;
+            const uint32_t ex = cta_excl_scan_256(v, s_warp, &tot);
+            if (i < nused) s_prefix[i] = (uint32_t)c0 + ex;
+            c0 += tot;
+        }
+        __syncthreads();
+        // the verdict of k_ff_scan, derived by every CTA of the frame alike
+        long long sz;
+        if (error_flag && *error_flag) sz = (long long)0x8000000000000000LL;                    // internal error
+        else if (nbytes > ucap) sz = -((long long)H.len + 2 * ((long long)c0 + nbytes + 2));    // upper bound of the need
+        else {
+            const long long need = (long long)H.len + (long long)c0 + nbytes + 2;
+            sz = need <= out_cap ? need : -need;
+        }
+        if (blockIdx.y == 0 && threadIdx.x == 0) sizes[f] = sz;
+        if (sz < 0) return;                                         // slot too small: leave it untouched
+    } else if (sizes[f] < 0) {
+        return;
+    }
     uint8_t *dst_frame = out + f * out_cap;
     if (seg == 0 && blockIdx.y == 0)
         for (int i = threadIdx.x; i < H.len; i += 256) dst_frame[i] = H.bytes[i];
-    uint8_t *dst_seg = dst_frame + H.len + segbase[vf];
+    uint8_t *dst_seg = dst_frame + H.len + (OWN_SCAN ? 0u : segbase[vf]);
     for (int ch = blockIdx.y; (long long)ch * kStuffChunk < nbytes; ch += gridDim.y) {
         const long long pos = (long long)ch * kStuffChunk + threadIdx.x * 16;
         uint32_t m = 0;
@@ -337,7 +366,7 @@ __global__ void __launch_bounds__(256) k_stuff_write(const uint8_t *__restrict__
         __syncthreads();
         const long long chunk_in = min((long long)kStuffChunk, nbytes - (long long)ch * kStuffChunk);
         const int n_out = (int)chunk_in + (int)tot;
-        uint8_t *dst = dst_seg + (long long)ch * kStuffChunk + ffpart[vf * chunks + ch];
+        uint8_t *dst = dst_seg + (long long)ch * kStuffChunk + (OWN_SCAN ? s_prefix[ch] : ffpart[vf * chunks + ch]);
         // head bytes up to 4-byte alignment, aligned words, tail bytes
         const int head = min(n_out, (int)((4 - ((uintptr_t)dst & 3)) & 3));
         if (threadIdx.x < head) dst[threadIdx.x] = s_out[threadIdx.x];
@@ -372,15 +401,20 @@ int launch_stuffing(const uint8_t *unstuffed, const int64_t *total_bits, uint32_
         k_ff_count<<<sgrid, 256, 0, st>>>(unstuffed, total_bits, ffpart, ucap, schunks);
         B2J_LAUNCH_CHECK("k_ff_count");
     }
-    k_ff_scan<<<(unsigned)n_frames, 256, 0, st>>>(ffpart, total_bits, segbase, sizes, ucap, out_cap, schunks, nseg, H.len,
-                                                  error_flag);
-    B2J_LAUNCH_CHECK("k_ff_scan");
     // enough CTAs per segment to fill the GPU a few times over, never more than the slot has chunks
     long long per_seg = (148 * 16 + nvf - 1) / nvf;
     if (per_seg > schunks) per_seg = schunks;
     if (per_seg < 1) per_seg = 1;
-    k_stuff_write<<<dim3((unsigned)nvf, (unsigned)per_seg), 256, 0, st>>>(unstuffed, total_bits, ffpart, segbase, sizes, out, ucap,
-                                                                          out_cap, schunks, nseg, rst_phase, H);
+    if (nseg == 1 && (size_t)schunks * sizeof(uint32_t) <= 32768) {
+        k_stuff_write<true><<<dim3((unsigned)nvf, (unsigned)per_seg), 256, (size_t)schunks * sizeof(uint32_t), st>>>(
+            unstuffed, total_bits, ffpart, segbase, sizes, out, ucap, out_cap, schunks, nseg, rst_phase, error_flag, H);
+    } else {
+        k_ff_scan<<<(unsigned)n_frames, 256, 0, st>>>(ffpart, total_bits, segbase, sizes, ucap, out_cap, schunks, nseg, H.len,
+                                                      error_flag);
+        B2J_LAUNCH_CHECK("k_ff_scan");
+        k_stuff_write<false><<<dim3((unsigned)nvf, (unsigned)per_seg), 256, 0, st>>>(unstuffed, total_bits, ffpart, segbase, sizes, out, ucap,
+                                                                                     out_cap, schunks, nseg, rst_phase, error_flag, H);
+    }
     B2J_LAUNCH_CHECK("k_stuff_write");
     return B2J_OK;
 }

@@ -44,6 +44,15 @@ constexpr int kSpinLimit = 1 << 22;
 #endif
 constexpr int kFusedSmem = (kCols * kPitch + kCap * kCols + kCols + kCols * 2 + kCols / 2 + 32 + 512 + 16) * 4 + B2J_ENT_SMEM_PAD;
 
+// The Annex-K code tables in the layout of HuffLut (dc[2][16], ac[2][256]) as a device constant: a CTA copies them with
+// coalesced loads (as a kernel parameter every lane read another word of the constant bank: 11 % of a single frame's time).
+static __device__ const uint32_t kHuffLutDev[544] = {
+#include "b2j_huff_lut.inc"
+};
+static const uint32_t kHuffLutHost[544] = {
+#include "b2j_huff_lut.inc"
+};
+
 struct FusedEntropyParams {
     const int16_t *coefs;
     uint8_t *unstuffed;
@@ -159,8 +168,7 @@ __device__ __forceinline__ void encode_block(uint32_t mlo, uint32_t mhi, int dif
 }
 
 template <bool EAGER, bool SEG>
-__global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant__ FusedEntropyParams P,
-                                                          const __grid_constant__ LutParam L)
+__global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant__ FusedEntropyParams P)
 {
     extern __shared__ __align__(16) uint32_t fsm[];
     uint32_t *s_coef = fsm;                                  // [kCols][kPitch]: coefficients as saturated bytes
@@ -174,7 +182,7 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t *my_ovf = P.overflow + (size_t)blockIdx.x * kOvfWords * kCols;
     const unsigned int total_chunks = (unsigned)P.chunks * (unsigned)P.e.n_frames;
-    load_lut(L, s_dc, s_ac);
+    for (int i = tid; i < 544; i += kChunk) s_dc[i] = kHuffLutDev[i];       // s_ac follows s_dc
   for (;;) {                                                          // persistent: one chunk per ticket
     __syncthreads();                                                  // shared memory of the previous chunk is free
     if (tid == 0) s_misc[4] = atomicAdd(P.ticket, 1u);
@@ -507,11 +515,12 @@ extern "C" int b2j_entropy_encode(const int16_t *coefs, const b2j_image_desc *de
         set_error("b2j_entropy_encode: internal header length mismatch");
         return B2J_E_ARG;
     }
-    const LutParam L = make_lut_param();
+    B2J_REQUIRE(memcmp(&host_huff_lut(), kHuffLutHost, sizeof kHuffLutHost) == 0, B2J_E_ARG,
+                "b2j_entropy_encode: b2j_huff_lut.inc is not the table the host code derives");
     cudaStream_t st = as_stream(stream);
     B2J_CUDA(cudaMemsetAsync(ws, 0, status_bytes, st));              // ticket, error flag, chunk status words
     const long long total = (long long)chunks * nvf;
-    using Kernel = void (*)(const FusedEntropyParams, const LutParam);
+    using Kernel = void (*)(const FusedEntropyParams);
     const bool seg = sp.nseg > 1;
     const int which = (zrl == B2J_ZRL_EAGER ? 0 : 2) + (seg ? 1 : 0);
     static const Kernel kernels[4] = {k_entropy_fused<true, false>, k_entropy_fused<true, true>, k_entropy_fused<false, false>,
@@ -523,7 +532,7 @@ extern "C" int b2j_entropy_encode(const int16_t *coefs, const b2j_image_desc *de
     long long slots = (long long)li.sms * li.per_sm;
     if (slots > kMaxSlots) slots = kMaxSlots;
     const unsigned grid = (unsigned)(total < slots ? total : slots);   // persistent CTAs, one scratch slot each
-    kernel<<<grid, kChunk, kFusedSmem, st>>>(P, L);
+    kernel<<<grid, kChunk, kFusedSmem, st>>>(P);
     B2J_LAUNCH_CHECK("k_entropy_fused");
     return launch_stuffing(P.unstuffed, P.total_bits, ffpart, sizes, out, ucap, out_cap, g.n_frames, H, P.error_flag, true, st,
                            sp.nseg, (opts >> 12) & 7);

@@ -73,7 +73,7 @@ def test_argument_errors_are_reported_not_raised_in_c(lj):
     assert cap >= 623 + 2 and cap % 16 == 0
     assert lib.b2j_encode_workspace_bytes(ctypes.byref(d), cap) > 3 * 4 * 128
     assert lib.b2j_encode_workspace_bytes(ctypes.byref(d), 10) == 0
-    assert lib.b2j_encode_launch_count(ctypes.byref(d)) == 4
+    assert lib.b2j_encode_launch_count(ctypes.byref(d)) == 3
 
 
 def test_operator_surface_matches_the_reference(lj):
