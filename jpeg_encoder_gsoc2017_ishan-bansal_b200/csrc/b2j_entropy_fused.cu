@@ -42,16 +42,36 @@ constexpr int kSpinLimit = 1 << 22;
 #ifndef B2J_ENT_SMEM_PAD
 #define B2J_ENT_SMEM_PAD 0
 #endif
-constexpr int kFusedSmem = (kCols * kPitch + kCap * kCols + kCols + kCols * 2 + kCols / 2 + 32 + 512 + 16) * 4 + B2J_ENT_SMEM_PAD;
+constexpr int kLutWords = 32 + 512 + 4;            // dc[2][16], ac[2][256] (walk layout), zrl_eob[2][2]: gen_huff_lut.py
+constexpr int kFusedSmem = (kCols * kPitch + kCap * kCols + kCols + kCols * 2 + kCols / 2 + kLutWords + 16) * 4 + B2J_ENT_SMEM_PAD;
 
 // The Annex-K code tables in the layout of HuffLut (dc[2][16], ac[2][256]) as a device constant: a CTA copies them with
 // coalesced loads (as a kernel parameter every lane read another word of the constant bank: 11 % of a single frame's time).
-static __device__ const uint32_t kHuffLutDev[544] = {
+static __device__ const uint32_t kHuffLutDev[kLutWords] = {
 #include "b2j_huff_lut.inc"
 };
-static const uint32_t kHuffLutHost[544] = {
+static const uint32_t kHuffLutHost[kLutWords] = {
 #include "b2j_huff_lut.inc"
 };
+
+// The same words derived from the host's code tables (the check before the first launch).
+static bool fused_lut_matches_host()
+{
+    const HuffLut &h = host_huff_lut();
+    uint32_t w[kLutWords];
+    memcpy(w, h.dc, 32 * sizeof(uint32_t));
+    for (int t = 0; t < 2; t++) {
+        for (int i = 0; i < 256; i++) {
+            const int size = (i & 15) + 1;
+            const uint32_t e = size <= 10 ? h.ac[t][(i & 0xF0) | size] : 0u;
+            const uint32_t len = e >> 16, code = e & 0xFFFFu;
+            w[32 + t * 256 + i] = (len ? code << (32 - len) : 0u) | ((len + size) << 8) | len;
+        }
+        w[544 + 2 * t] = h.ac[t][0xF0];
+        w[545 + 2 * t] = h.ac[t][0x00];
+    }
+    return memcmp(w, kHuffLutHost, sizeof w) == 0;
+}
 
 struct FusedEntropyParams {
     const int16_t *coefs;
@@ -81,47 +101,73 @@ __device__ __forceinline__ void st_volatile(unsigned long long *p, unsigned long
     asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+__device__ __forceinline__ uint32_t sm_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ int lds_s8(uint32_t a)
+{
+    int v;
+    asm volatile("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
 // Packs fields MSB-first into a private column of shared memory: word k of column c lives at
-// col[k * kCols] (word-interleaved, so any mix of k across the lanes of a warp is conflict free).
+// col[k * kCols] (word-interleaved, so any mix of k across the lanes of a warp is conflict free).  The column is walked
+// with a 32-bit shared address; words kCap.. continue, at the same stride, in a global scratch column.
+constexpr uint32_t kColStride = kCols * 4u;       // bytes between consecutive words of a column
 struct PrivSink {
-    uint32_t *col;                // shared column (first kCap words)
+    uint32_t p0, p;               // shared address of the column's first word, and of the word being filled (virtual past kCap words)
     uint32_t *ovf;                // global scratch column (words kCap..)
     uint32_t acc;                 // pending bits, left aligned
     int nb;                       // number of pending bits (< 32)
-    int k;                        // words already stored
-    __device__ __forceinline__ void begin(uint32_t *c, uint32_t *o) { col = c; ovf = o; acc = 0u; nb = 0; k = 0; }
-    __device__ __forceinline__ void store(uint32_t w)
+    __device__ __forceinline__ void begin(uint32_t *c, uint32_t *o) { p0 = p = sm_addr(c); ovf = o; acc = 0u; nb = 0; }
+    __device__ __forceinline__ void store()
     {
-        if (k < kCap) col[k * kCols] = w;
-        else if (k < kPrivWords) ovf[(k - kCap) * kCols] = w;        // (coefficients outside the JPEG range: drop, never write past the column)
+        if (p < p0 + kCap * kColStride) sts_u32(p, acc);
+        else if (p < p0 + kPrivWords * kColStride)                   // (coefficients outside the JPEG range: drop, never write past the column)
+            *reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(ovf) + (p - p0 - kCap * kColStride)) = acc;
     }
-    __device__ __forceinline__ uint32_t load(int i) const { return i < kCap ? col[i * kCols] : ovf[(i - kCap) * kCols]; }
-    __device__ __forceinline__ void put(uint32_t val, int len)      // 1 <= len <= 32, val < 2^len
+    __device__ __forceinline__ uint32_t load(int i) const { return i < kCap ? lds_u32(p0 + (uint32_t)i * kColStride) : ovf[(i - kCap) * kCols]; }
+    __device__ __forceinline__ void put_left(uint32_t x, int len)   // x: the field left aligned, 0 <= len <= 32
     {
-        const uint32_t x = val << (32 - len);                        // left aligned field
         acc |= x >> nb;
-        const int n = nb + len;
-        if (n >= 32) {
-            store(acc);
-            k++;
-            acc = nb ? x << (32 - nb) : 0u;
-            nb = n - 32;
-        } else {
-            nb = n;
+        const uint32_t spill = __funnelshift_r(0u, x, nb);           // the bits that do not fit: x << (32 - nb), 0 for nb = 0
+        nb += len;
+        if (nb >= 32) {
+            store();
+            p += kColStride;
+            acc = spill;
+            nb -= 32;
         }
     }
-    __device__ __forceinline__ int bits() const { return k * 32 + nb; }
-    __device__ __forceinline__ void flush() { store(acc); }         // zero padded partial word
+    __device__ __forceinline__ void put(uint32_t val, int len)      // 1 <= len <= 32, val < 2^len
+    {
+        put_left(val << (32 - len), len);
+    }
+    __device__ __forceinline__ int words() const { return (int)((p - p0) / kColStride); }
+    __device__ __forceinline__ int bits() const { return words() * 32 + nb; }
+    __device__ __forceinline__ void flush() { store(); }            // zero padded partial word
 };
 
 // Sparse walk of one block: only the non-zero AC positions (set bits of the mask) are visited.
 // blk: the block's 64 coefficients as saturated bytes in shared memory; a byte at either end of the range (+127 / -128)
 // stands for "read the int16 from the coefficient array" (g16: the block in global memory; rare at any quality).
+// lut_ac: the walk layout of gen_huff_lut.py (index run << 4 | size - 1; code left aligned, field length in byte 1,
+// code length in the low bits); zrl_eob: the two codes without amplitude bits as (length << 16) | code.
 // With PARTIAL the walk stops once 32 bits are out (lookahead blocks only have to complete the previous word).
+// Shared memory through 32-bit addresses; ONE loop for all lanes of a warp.  (A short first loop for the common case - no
+// ZRL, words still inside the shared column - followed by this general one was 0.90 instead of 0.93 ms on the headline
+// batch, but lanes of a warp in different loops run one after the other: 8K noise 2.5 -> 4.0 ms.  Picking the variant per
+// warp from the symbol counts cost more in code size than it gave: profiles/r02/experiments.txt.)
 template <bool EAGER, bool PARTIAL>
 __device__ __forceinline__ void encode_block(uint32_t mlo, uint32_t mhi, int diff, const uint32_t *blk, const int16_t *__restrict__ g16,
                                              const uint32_t *__restrict__ lut_dc, const uint32_t *__restrict__ lut_ac,
-                                             PrivSink &sink)
+                                             const uint32_t *__restrict__ zrl_eob, int *error_flag, PrivSink &sink)
 {
     {
         const int s = bit_size(diff);
@@ -129,34 +175,43 @@ __device__ __forceinline__ void encode_block(uint32_t mlo, uint32_t mhi, int dif
         const uint32_t extra = (uint32_t)(diff < 0 ? diff - 1 : diff) & ((1u << s) - 1u);
         sink.put(((e & 0xFFFFu) << s) | extra, (int)(e >> 16) + s);
     }
-    const uint32_t zrl = lut_ac[0xF0], eob = lut_ac[0x00];
-    const int8_t *c8 = reinterpret_cast<const int8_t *>(blk);
+    const uint32_t blk_s = sm_addr(blk), lut_s = sm_addr(lut_ac);
+    const uint32_t zrl = zrl_eob[0], eob = zrl_eob[1];
     int prev = 0;
-    uint32_t m = mlo & ~1u;                                         // position 0 is the DC
+    uint32_t m = mlo & ~1u, mnext = mhi;                            // position 0 is the DC
     int base = 0;
-#pragma unroll 1
-    for (int half = 0; half < 2; half++) {
+    for (;;) {
 #pragma unroll 1
         while (m) {
-            if (PARTIAL && sink.k > 0) return;
+            if (PARTIAL && sink.p != sink.p0) return;
             const int z = base + __ffs((int)m) - 1;
             m &= m - 1u;
-            int v = (int)c8[z];
-            if ((unsigned)(v + 127) >= 254u) v = (int)__ldg(g16 + z);          // saturated byte: the real value
-            const int run = z - prev - 1;
+            int v = lds_s8(blk_s + (uint32_t)z);
+            if ((unsigned)(v + 127) >= 254u) {                      // saturated byte: the real value
+                v = (int)__ldg(g16 + z);
+                if (abs(v) > 1023) atomicExch(error_flag, 1);       // no baseline table codes it -> every sizes[] becomes INT64_MIN
+            }
+            int run = z - prev - 1;
             prev = z;
             if (run >= 16) {                                        // ZRLs in front of a non-zero: same for both policies
 #pragma unroll 1
                 for (int n = run >> 4; n > 0; n--) sink.put(zrl & 0xFFFFu, (int)(zrl >> 16));
+                run &= 15;
             }
-            const int s = bit_size(v);
-            const uint32_t e = lut_ac[((run & 15) << 4) | s];
-            sink.put(((e & 0xFFFFu) << s) | ((uint32_t)(v + (v >> 31)) & ((1u << s) - 1u)), (int)(e >> 16) + s);
+            // amplitude bits (v - 1 for negative values, T.81 F.1.2.2) left aligned by the position of the top bit of |v|
+            uint32_t top;
+            asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(abs(v)));     // size - 1
+            const uint32_t e = lds_u32(lut_s + (uint32_t)run * 64u + top * 4u);
+            const uint32_t amp = (uint32_t)(v + (v >> 31)) << (31u - top);
+            // (the shift uses the low five bits of e, the code length; byte 1 is the length of the field)
+            sink.put_left((e & 0xFFFF0000u) | __funnelshift_r(amp, 0u, e), (int)__byte_perm(e, 0u, 0x4441));
         }
-        m = mhi;
+        if (base) break;
+        m = mnext;
+        mnext = 0u;
         base = 32;
     }
-    if (PARTIAL && sink.k > 0) return;
+    if (PARTIAL && sink.p != sink.p0) return;
     const int t = 63 - prev;                                        // trailing zeros
     if (EAGER) {                                                    // rlecore.py:101-114
 #pragma unroll 1
@@ -167,8 +222,11 @@ __device__ __forceinline__ void encode_block(uint32_t mlo, uint32_t mhi, int dif
     }
 }
 
+#ifndef B2J_ENT_MIN_CTAS
+#define B2J_ENT_MIN_CTAS 12
+#endif
 template <bool EAGER, bool SEG>
-__global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant__ FusedEntropyParams P)
+__global__ void __launch_bounds__(kChunk, B2J_ENT_MIN_CTAS) k_entropy_fused(const __grid_constant__ FusedEntropyParams P)
 {
     extern __shared__ __align__(16) uint32_t fsm[];
     uint32_t *s_coef = fsm;                                  // [kCols][kPitch]: coefficients as saturated bytes
@@ -177,12 +235,14 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
     uint32_t *s_mask = s_nbits + kCols;                      // [kCols][2]: eight mask bytes per block
     int16_t *s_dc16 = reinterpret_cast<int16_t *>(s_mask + kCols * 2);   // [kCols]: the DC coefficients, unsaturated
     uint32_t *s_dc = s_mask + kCols * 2 + kCols / 2;         // [2][16]
-    uint32_t *s_ac = s_dc + 32;                              // [2][256]
-    uint32_t *s_misc = s_ac + 512;                           // warp sums [4], ticket, prefix lo/hi
+    uint32_t *s_ac = s_dc + 32;                              // [2][256], the walk's layout
+    uint32_t *s_ze = s_ac + 512;                             // [2][2]: ZRL and EOB
+    uint32_t *s_misc = s_ze + 4;                             // warp sums [4], ticket, prefix lo/hi
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t *my_ovf = P.overflow + (size_t)blockIdx.x * kOvfWords * kCols;
     const unsigned int total_chunks = (unsigned)P.chunks * (unsigned)P.e.n_frames;
-    for (int i = tid; i < 544; i += kChunk) s_dc[i] = kHuffLutDev[i];       // s_ac follows s_dc
+    for (int i = tid; i < kLutWords; i += kChunk) s_dc[i] = kHuffLutDev[i];   // s_ac and s_ze follow s_dc
+    const unsigned bpm_recip = 65536u / (unsigned)P.e.bpm + 1u;                // n / bpm for n < 4096
   for (;;) {                                                          // persistent: one chunk per ticket
     __syncthreads();                                                  // shared memory of the previous chunk is free
     if (tid == 0) s_misc[4] = atomicAdd(P.ticket, 1u);
@@ -218,7 +278,7 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
         uint8_t *mask8 = reinterpret_cast<uint8_t *>(s_mask);
         const int npieces = nall * 8;
 #ifndef B2J_ENT_LOAD_BATCH
-#define B2J_ENT_LOAD_BATCH 3
+#define B2J_ENT_LOAD_BATCH 2
 #endif
         // the loads of a batch are issued together: the phase is bound by memory latency (9 dependent round trips
         // per chunk otherwise)
@@ -262,6 +322,9 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
             }
         }
     }
+    // k0: position of column 0 inside its MCU
+    const int k0 = (int)((unsigned)b0 % (unsigned)e.bpm);
+    auto mcu_pos = [&](int col) { const unsigned a = (unsigned)(k0 + col); return (int)(a - ((a * bpm_recip) >> 16) * (unsigned)e.bpm); };
     __syncthreads();
 
     // ---- 2. one walk per block: private packed bits + bit count
@@ -269,38 +332,41 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
         if (b >= b0) return (int)s_dc16[(int)(b - b0)];
         return b >= 0 ? (int)fc[b * 64] : 0;
     };
-    auto prev_index = [&](long long b) -> long long {
-        const int k = (int)(b % e.bpm);
+    auto prev_index = [&](long long b, int k) -> long long {        // k: position of block b inside its MCU
         if (k < e.hv) return k > 0 ? b - 1 : b - e.bpm + e.hv - 1;
         return b - e.bpm;
     };
+    const int col = tid;                                             // the column this thread walks and composes
     PrivSink sink;
-    sink.begin(s_priv + tid, my_ovf + tid);
+    sink.begin(s_priv + col, my_ovf + col);
     int mybits = 0;
     if (tid < nown) {
-        const long long b = b0 + tid;
-        const uint32_t *blk = s_coef + tid * kPitch;
-        const int chroma = (int)(b % e.bpm) >= e.hv;
-        const int diff = (int)s_dc16[tid] - dc_of(prev_index(b));
-        encode_block<EAGER, false>(s_mask[tid * 2], s_mask[tid * 2 + 1], diff, blk, fc + b * 64, s_dc + 16 * chroma, s_ac + 256 * chroma, sink);
+        const long long b = b0 + col;
+        const uint32_t *blk = s_coef + col * kPitch;
+        const int k = mcu_pos(col), chroma = k >= e.hv;
+        const int diff = (int)s_dc16[col] - dc_of(prev_index(b, k));
+        encode_block<EAGER, false>(s_mask[col * 2], s_mask[col * 2 + 1], diff, blk, fc + b * 64, s_dc + 16 * chroma, s_ac + 256 * chroma,
+                                   s_ze + 2 * chroma, P.error_flag, sink);
         sink.flush();
-        mybits = sink.bits();
-        if (mybits > (kPrivWords - 1) * 32) {                       // only with coefficients no baseline table can code
+        int bits = sink.bits();
+        if (bits > (kPrivWords - 1) * 32) {                         // only with coefficients no baseline table can code
             atomicExch(P.error_flag, 1);                            // -> every sizes[] becomes INT64_MIN
-            mybits = (kPrivWords - 1) * 32;
+            bits = (kPrivWords - 1) * 32;
         }
-        s_nbits[tid] = (uint32_t)mybits;
+        s_nbits[col] = (uint32_t)bits;
+        mybits = bits;
     }
     // the lookahead blocks only have to supply the bits that complete this chunk's last word
     if (tid < kLookahead && kChunk + tid < nall && !last) {
         const int colidx = kChunk + tid;
         const long long b = b0 + colidx;
         const uint32_t *blk = s_coef + colidx * kPitch;
-        const int chroma = (int)(b % e.bpm) >= e.hv;
-        const int diff = (int)s_dc16[colidx] - dc_of(prev_index(b));
+        const int k = mcu_pos(colidx), chroma = k >= e.hv;
+        const int diff = (int)s_dc16[colidx] - dc_of(prev_index(b, k));
         PrivSink sk;
         sk.begin(s_priv + colidx, nullptr);
-        encode_block<EAGER, true>(s_mask[colidx * 2], s_mask[colidx * 2 + 1], diff, blk, fc + b * 64, s_dc + 16 * chroma, s_ac + 256 * chroma, sk);
+        encode_block<EAGER, true>(s_mask[colidx * 2], s_mask[colidx * 2 + 1], diff, blk, fc + b * 64, s_dc + 16 * chroma, s_ac + 256 * chroma,
+                                  s_ze + 2 * chroma, P.error_flag, sk);
         sk.flush();
         s_nbits[colidx] = (uint32_t)sk.bits();                      // >= 32 when the walk was cut short
     }
@@ -360,10 +426,10 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
     // that is not always the last block's thread, nor even a thread of the last chunk (a short
     // tail of 4-6 bit blocks can sit entirely inside a word owned by the previous chunk, which
     // sees those blocks as its lookahead columns).
-    const uint32_t total = (uint32_t)mybits;
     const bool reaches_end = bl >= nblk;                             // columns 0..nall-1 run to the stream's end
-    if (last && tid == nown - 1) P.total_bits[f] = (int64_t)((uint32_t)E + excl + total);
     if (tid < nown) {
+        const uint32_t total = (uint32_t)mybits;
+        if (last && col == nown - 1) P.total_bits[f] = (int64_t)((uint32_t)E + excl + total);
         const uint32_t G = (uint32_t)E + excl;
         uint32_t *dst = reinterpret_cast<uint32_t *>(P.unstuffed + (long long)f * P.ucap);
         const uint32_t wcap = (uint32_t)(P.ucap >> 2);
@@ -373,6 +439,7 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
         const uint32_t wend = (G + total + 31u) >> 5;
         int rel = (int)((w << 5) - G);                               // first bit of word w inside my block
         uint32_t a = sink.load(rel >> 5);
+        uint32_t n_ff = 0u, ff_chunk = w >> 10;
 #pragma unroll 1
         for (; w < wend; w++, rel += 32) {
             const int k = rel >> 5, sh = rel & 31;
@@ -383,7 +450,7 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
             if (have0 < 32) {                                        // complete the word with the following blocks' first bits
                 int have = have0;
 #pragma unroll 1
-                for (int nb = tid + 1; have < 32 && nb < nsucc; nb++) {
+                for (int nb = col + 1; have < 32 && nb < nsucc; nb++) {
                     v |= s_priv[nb] >> have;
                     have += (int)s_nbits[nb];
                 }
@@ -395,12 +462,18 @@ __global__ void __launch_bounds__(kChunk) k_entropy_fused(const __grid_constant_
             if (w < wcap) {
                 dst[w] = __byte_perm(v, 0u, 0x0123);                 // big-endian bytes
                 const uint32_t z = ~v;                               // a zero byte of z is a 0xFF byte of the stream
-                if ((z - 0x01010101u) & ~z & 0x80808080u) {
-                    const uint32_t n = ((z & 0xFFu) == 0u) + ((z & 0xFF00u) == 0u) + ((z & 0xFF0000u) == 0u) + ((z >> 24) == 0u);
-                    atomicAdd(ffp + (w >> 10), n);                   // 1024 words per stuffing chunk
+                if ((z - 0x01010101u) & ~z & 0x80808080u) {          // (some byte is zero; which ones, exactly:)
+                    const uint32_t zb = ~(((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z | 0x7F7F7F7Fu);
+                    if ((w >> 10) != ff_chunk) {                     // 1024 words per stuffing chunk: a block can straddle two
+                        if (n_ff) atomicAdd(ffp + ff_chunk, n_ff);
+                        n_ff = 0u;
+                        ff_chunk = w >> 10;
+                    }
+                    n_ff += (uint32_t)__popc(zb);
                 }
             }
         }
+        if (n_ff) atomicAdd(ffp + ff_chunk, n_ff);                   // one atomic per block with 0xFF bytes, not one per word
     }
   }
 }
@@ -515,8 +588,8 @@ extern "C" int b2j_entropy_encode(const int16_t *coefs, const b2j_image_desc *de
         set_error("b2j_entropy_encode: internal header length mismatch");
         return B2J_E_ARG;
     }
-    B2J_REQUIRE(memcmp(&host_huff_lut(), kHuffLutHost, sizeof kHuffLutHost) == 0, B2J_E_ARG,
-                "b2j_entropy_encode: b2j_huff_lut.inc is not the table the host code derives");
+    static const bool lut_ok = fused_lut_matches_host();
+    B2J_REQUIRE(lut_ok, B2J_E_ARG, "b2j_entropy_encode: b2j_huff_lut.inc is not the table the host code derives");
     cudaStream_t st = as_stream(stream);
     B2J_CUDA(cudaMemsetAsync(ws, 0, status_bytes, st));              // ticket, error flag, chunk status words
     const long long total = (long long)chunks * nvf;
