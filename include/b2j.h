@@ -171,6 +171,27 @@ int b2j_ingest(const uint8_t *src, int layout, int32_t width, int32_t height, in
                int64_t src_row_stride, int64_t src_plane_stride, int64_t src_frame_stride,
                uint8_t *rgb, void *stream);
 
+/* [ext] PNG ingest on the device.  replaces: PIL decoding the file on the host,
+ * test/model/enc_frame.py:7 (`Image.open`) and test/common.py:47-51 (`img.getdata()`).
+ * The host walks the chunk list (b2j_png_info: size, samples per pixel and the total IDAT payload of one
+ * file held in host memory); b2j_png_decode copies the zlib streams of n_files equally sized files to the
+ * device, where one warp per file inflates (RFC 1951: stored, fixed and dynamic blocks) and undoes the
+ * scanline filters (None, Sub, Up, Average, Paeth), writing packed RGB frames n_files x height x width x 3
+ * (alpha dropped as enc_frame.py:8-10 does, grey replicated) - the input of b2j_fused_block / b2j_encode.
+ * Decoded on the device: 8 bits per sample, colour types 0 / 2 / 6 (channels 1 / 3 / 4), non-interlaced;
+ * any other file returns B2J_E_SHAPE (decode it with PIL as the reference does, then b2j_ingest).
+ * status_host (may be NULL; n_files entries, the call then waits for the stream): 0 = decoded, otherwise
+ * 1 bad zlib header, 2 bad Huffman code / distance, 3 more data than the image holds, 4 stream ends early,
+ * 5 less data than the image holds, 6 unknown filter type; the frame of such a file is undefined.
+ * The call returns after the host-to-device copy of the streams; the kernels run on `stream`. */
+int b2j_png_info(const uint8_t *png_host, int64_t png_bytes, int32_t *width, int32_t *height,
+                 int32_t *channels, int64_t *zlib_bytes);
+size_t b2j_png_workspace_bytes(int32_t width, int32_t height, int32_t channels, int32_t n_files,
+                               int64_t max_zlib_bytes);
+int b2j_png_decode(const uint8_t *const *png_host, const int64_t *png_bytes, int32_t n_files,
+                   int32_t width, int32_t height, int32_t channels, void *workspace,
+                   size_t workspace_bytes, uint8_t *rgb, int32_t *status_host, void *stream);
+
 /* [ext] plane subsampling with the same pair mean, horizontally (422) and then
  * vertically (420).  in: height x width, out: (height/v) x (width/2). */
 int b2j_chroma_subsample(const uint8_t *in, uint8_t *out, int32_t height, int32_t width,

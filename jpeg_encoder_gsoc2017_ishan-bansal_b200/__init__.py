@@ -10,7 +10,7 @@ from .common import (Packet, coef, rgb_layout, ycbcr444_layout, ycbcr422_layout,
 from .core import (RGB2YCbCr, YCbCr2RGB, rgb2ycbcr_coefs, ycbcr2rgb_coefs, YCbCr444to422, YCbCr422to444, YCbCr444to420, DCT, Quantization, quant_values,  # noqa: F401
                    ZigZag, zigzag_order, zigzag_rom, RunLength, EntropyCoder, RLEMain, Huffman, BitPack)
 from . import model                                                    # noqa: F401
-from .ingest import to_rgb, read_image                                 # noqa: F401
+from .ingest import to_rgb, read_image, decode_png, png_info                                 # noqa: F401
 from .encoder import (JpegEncoder, MultiGpuJpegEncoder, ShardedJpegEncoder, shard_range, gather_sizes, gather_streams,   # noqa: F401
                       band_plan, assemble_bands)
 

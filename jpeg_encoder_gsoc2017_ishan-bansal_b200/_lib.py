@@ -58,6 +58,9 @@ SIGNATURES = {
     "b2j_rle_code": (c_int, [_P, _P, _P, c_int64, _P]),
     "b2j_dct_fixed": (c_int, [_P, _P, c_int64, _P]),
     "b2j_ingest": (c_int, [_P, c_int, c_int32, c_int32, c_int32, c_int64, c_int64, c_int64, _P, _P]),
+    "b2j_png_info": (c_int, [_P, c_int64, _P, _P, _P, _P]),
+    "b2j_png_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32, c_int64]),
+    "b2j_png_decode": (c_int, [_P, _P, c_int32, c_int32, c_int32, c_int32, _P, c_size_t, _P, _P, _P]),
     "b2j_fused_block": (c_int, [_P, _DESC, _P, _P, _P, c_int, _P]),
     "b2j_block_bits": (c_int, [_P, _DESC, c_int, _P, _P]),
     "b2j_scan_workspace_bytes": (c_size_t, [_DESC]),

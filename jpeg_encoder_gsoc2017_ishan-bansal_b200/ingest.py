@@ -2,10 +2,14 @@
 
 The reference reads images on the host with PIL and unpacks them in Python
 (test/model/enc_frame.py:7-10 takes `arr[..., 0..2]`; test/common.py:47-51 unzips
-`img.getdata()`).  Here the file is still decoded by PIL on the host (`read_image`), but
-every layout conversion runs on the GPU (`to_rgb`, C entry point `b2j_ingest`), so a
-frame grabber's BGRA or planar buffers can be fed to `JpegEncoder` without a host pass.
+`img.getdata()`).  Here 8-bit grey / RGB / RGBA PNG files are decoded on the GPU (`decode_png`,
+C entry point `b2j_png_decode`: inflate + scanline filters, one warp per file, a batch of files
+per call); `read_image` uses it for such files and PIL for everything else, and every layout
+conversion runs on the GPU (`to_rgb`, C entry point `b2j_ingest`), so a frame grabber's BGRA or
+planar buffers can be fed to `JpegEncoder` without a host pass.
 """
+import ctypes
+
 import torch
 
 from . import _lib
@@ -57,12 +61,73 @@ def to_rgb(x, layout="rgb", stream=None):
     return out[0] if single else out
 
 
-def read_image(path, device="cuda"):
-    """Image file -> CUDA uint8 RGB tensor (H, W, 3).  PIL decodes on the host (as the reference
-    does); palette / grey / RGBA files are brought to RGB on the GPU."""
+PNG_STATUS = {1: "bad zlib header", 2: "bad Huffman code or distance", 3: "more data than the image holds",
+              4: "stream ends early", 5: "less data than the image holds", 6: "unknown filter type"}
+
+
+def png_info(data):
+    """(width, height, channels, zlib_bytes) of a PNG file held in `data` (bytes); ValueError for files the
+    device decoder does not take (anything but 8-bit grey / RGB / RGBA, non-interlaced)."""
+    w, h, c, z = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int64()
+    data = bytes(data)
+    _lib.check(_lib.lib().b2j_png_info(ctypes.cast(ctypes.c_char_p(data), ctypes.c_void_p), len(data), ctypes.byref(w), ctypes.byref(h),
+                                       ctypes.byref(c), ctypes.byref(z)))
+    return w.value, h.value, c.value, z.value
+
+
+def decode_png(files, device="cuda", stream=None):
+    """PNG files (a list of bytes objects or paths, all of one size and colour type) -> CUDA uint8 RGB tensor
+    (N, H, W, 3), decoded on the GPU: the host only gathers the IDAT payloads.  Raises ValueError when a
+    stream is damaged (the message names the file and what the decoder found)."""
+    require_cuda()
+    blobs = []
+    for f in files:
+        if isinstance(f, (bytes, bytearray, memoryview)):
+            blobs.append(bytes(f))
+        else:
+            with open(f, "rb") as fh:
+                blobs.append(fh.read())
+    if not blobs:
+        raise ValueError("decode_png: no files")
+    infos = [png_info(b) for b in blobs]
+    w, h, c, _ = infos[0]
+    n = len(blobs)
+    dev = torch.device(device)
+    L = _lib.lib()
+    ptrs = (ctypes.c_void_p * n)(*[ctypes.cast(ctypes.c_char_p(b), ctypes.c_void_p) for b in blobs])   # (no copies: `blobs` stays alive)
+    lens = (ctypes.c_int64 * n)(*[len(b) for b in blobs])
+    status = (ctypes.c_int32 * n)()
+    with torch.cuda.device(dev):
+        need = L.b2j_png_workspace_bytes(w, h, c, n, max(i[3] for i in infos))
+        ws = torch.empty((need + 256,), dtype=torch.uint8, device=dev)
+        wp = (ws.data_ptr() + 255) & ~255
+        out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
+        _lib.check(L.b2j_png_decode(ptrs, lens, n, w, h, c, wp, need, out.data_ptr(), status, stream_ptr(stream)))
+    for i, st in enumerate(status):
+        if st:
+            raise ValueError("decode_png: file %d: %s" % (i, PNG_STATUS.get(st, "status %d" % st)))
+    return out
+
+
+def read_image(path, device="cuda", decoder="auto"):
+    """Image file -> CUDA uint8 RGB tensor (H, W, 3).  decoder "auto": 8-bit grey / RGB / RGBA non-interlaced
+    PNG files are decoded on the GPU (`decode_png`), any other file by PIL on the host (as the reference
+    does), its palette / grey / RGBA pixels then brought to RGB on the GPU; "device" insists on the GPU
+    decoder (ValueError for other files), "pil" on the host one."""
+    if decoder not in ("auto", "device", "pil"):
+        raise ValueError("decoder must be auto, device or pil")
+    require_cuda()
+    if decoder != "pil":
+        with open(path, "rb") as fh:
+            data = fh.read()
+        try:
+            png_info(data)
+            return decode_png([data], device)[0]
+        except (ValueError, RuntimeError):
+            if decoder == "device":
+                raise
     from PIL import Image
     import numpy as np
-    require_cuda()
     img = Image.open(path)
     if img.mode not in ("RGB", "RGBA", "L"):
         img = img.convert("RGBA" if "A" in img.getbands() else "RGB")

@@ -8,7 +8,7 @@ SRC=$ROOT/jpeg_encoder_gsoc2017_ishan-bansal_b200/csrc
 OUT=$ROOT/jpeg_encoder_gsoc2017_ishan-bansal_b200/variants
 TMP=$(mktemp -d)
 ARCH="-gencode arch=compute_100a,code=sm_100a"
-for f in b2j_common b2j_stages b2j_fused b2j_entropy b2j_entropy_fused b2j_encode; do
+for f in b2j_common b2j_stages b2j_fused b2j_entropy b2j_entropy_fused b2j_encode b2j_png; do
   nvcc $ARCH -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC -Xptxas -v $FLAGS -c -o $TMP/$f.o $SRC/$f.cu 2> $TMP/$f.log &
 done
 wait
