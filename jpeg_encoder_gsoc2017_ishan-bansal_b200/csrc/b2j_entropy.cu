@@ -291,8 +291,11 @@ __global__ void __launch_bounds__(256) k_ff_scan(uint32_t *__restrict__ ffpart, 
 // OWN_SCAN (frames of one segment, i.e. no restart intervals): the CTA scans the 0xFF counts of its frame's chunks itself
 // (a few hundred values) and derives the file size and the capacity verdict - no k_ff_scan launch in front; ffpart then
 // holds the raw counts and segbase is not used.
+#ifndef B2J_STUFF_MIN_CTAS
+#define B2J_STUFF_MIN_CTAS 6
+#endif
 template <bool OWN_SCAN>
-__global__ void __launch_bounds__(256) k_stuff_write(const uint8_t *__restrict__ unstuffed, const int64_t *__restrict__ total_bits,
+__global__ void __launch_bounds__(256, B2J_STUFF_MIN_CTAS) k_stuff_write(const uint8_t *__restrict__ unstuffed, const int64_t *__restrict__ total_bits,
                                                      const uint32_t *__restrict__ ffpart, const uint32_t *__restrict__ segbase,
                                                      int64_t *__restrict__ sizes, uint8_t *__restrict__ out, long long ucap,
                                                      long long out_cap, int chunks, int nseg, int rst_phase,
@@ -300,7 +303,12 @@ __global__ void __launch_bounds__(256) k_stuff_write(const uint8_t *__restrict__
 {
     extern __shared__ uint32_t s_prefix[];                          // OWN_SCAN: exclusive prefix of the frame's 0xFF counts
     __shared__ uint32_t s_warp[8];
-    __shared__ __align__(16) uint8_t s_out[2 * kStuffChunk + 16];
+    __shared__ __align__(16) uint8_t s_out[2 * kStuffChunk + 64];
+    __shared__ __align__(16) uint4 s_in[256];                        // the chunk's pieces, for the byte-wise pass
+    __shared__ uint32_t s_head[257];                                // first three stuffed bytes of every piece
+    __shared__ uint16_t s_o[256], s_list[256];                      // staging offset of every piece; pieces of the byte-wise pass
+    __shared__ uint32_t s_nlist;
+    __shared__ uint32_t s_warp2[2][8];
     const long long vf = blockIdx.x;
     const long long f = vf / nseg;
     const int seg = (int)(vf % nseg);
@@ -334,50 +342,112 @@ __global__ void __launch_bounds__(256) k_stuff_write(const uint8_t *__restrict__
     if (seg == 0 && blockIdx.y == 0)
         for (int i = threadIdx.x; i < H.len; i += 256) dst_frame[i] = H.bytes[i];
     uint8_t *dst_seg = dst_frame + H.len + (OWN_SCAN ? 0u : segbase[vf]);
-    for (int ch = blockIdx.y; (long long)ch * kStuffChunk < nbytes; ch += gridDim.y) {
-        const long long pos = (long long)ch * kStuffChunk + threadIdx.x * 16;
-        uint32_t m = 0;
-        int nvalid = 0;
-        uint4 q = make_uint4(0, 0, 0, 0);
+    // A chunk is 256 pieces of 16 bytes, one per thread.  Staging offset of piece t = (dst & 15) + 16 t + (0xFF bytes in
+    // front of it): shared and global memory then agree modulo 16 and the chunk leaves as 16-byte vectors.  Every aligned
+    // word of the staging area has ONE writer, the piece in which its first byte lies (that piece appends the first
+    // bytes of its successor's stuffed stream, s_head, to fill its last word).  Pieces without a 0xFF (94 %) store four
+    // words; the others are listed and written byte by byte by the first threads of the CTA in a second pass, so the
+    // byte loop runs in one warp per chunk instead of in every warp that holds such a piece (86 % of them).
+    const int t = threadIdx.x;
+    auto fetch = [&](int ch_) {                                      // (a chunk's piece is loaded one iteration ahead)
+        const long long pos_ = (long long)ch_ * kStuffChunk + t * 16;
+        return pos_ < nbytes ? __ldg(reinterpret_cast<const uint4 *>(unstuffed + vf * ucap + pos_)) : make_uint4(0, 0, 0, 0);
+    };
+    uint4 q_next = fetch(blockIdx.y);
+    int parity = 0;
+    for (int ch = blockIdx.y; (long long)ch * kStuffChunk < nbytes; ch += gridDim.y, parity ^= 1) {
+        const long long pos = (long long)ch * kStuffChunk + t * 16;
+        uint4 q = q_next;
+        q_next = fetch(ch + (int)gridDim.y);
         if (pos < nbytes) {
-            nvalid = (int)min(16LL, nbytes - pos);
-            q = *reinterpret_cast<const uint4 *>(unstuffed + vf * ucap + pos);
-            m = ff_mask16(q, nvalid);
-        }
-        uint32_t tot;
-        const uint32_t ex = cta_excl_scan_256(__popc(m), s_warp, &tot);
-        // stuffed bytes of this thread into shared memory at its chunk-relative offset
-        {
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-            int o = threadIdx.x * 16 + (int)ex;
-            if (tot == 0u && nvalid == 16) {                        // no 0xFF in the whole chunk: plain copy
-                *reinterpret_cast<uint4 *>(s_out + o) = q;
-            } else {
+            const int nvalid = (int)min(16LL, nbytes - pos);
+            if (nvalid < 16) {                                      // the stream's last piece: bytes past its end are not data
+                uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    if (i < nvalid) {
-                        const uint8_t b = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
-                        s_out[o++] = b;
-                        if (b == 0xFF) s_out[o++] = 0;
-                    }
+                for (int i = 0; i < 4; i++) {
+                    const int keep = min(max(nvalid - 4 * i, 0), 4);
+                    w[i] = keep == 4 ? w[i] : (keep == 0 ? 0u : w[i] & ((1u << (8 * keep)) - 1u));
                 }
+                q = make_uint4(w[0], w[1], w[2], w[3]);
             }
         }
-        __syncthreads();
+        // 0x80 in every 0xFF byte
+        auto ff_bits = [](uint32_t w) { return ~((~w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) & w & 0x80808080u; };
+        const uint32_t f0 = ff_bits(q.x), f1 = ff_bits(q.y), f2 = ff_bits(q.z), f3 = ff_bits(q.w);
+        const uint32_t cnt = (uint32_t)(__popc(f0) + __popc(f1) + __popc(f2) + __popc(f3));
+        // first three bytes of this piece's stuffed stream: [FF 00 b1], [b0 FF 00] or [b0 b1 b2]
+        s_head[t] = (f0 & 0x80u) ? (0xFFu | ((q.x & 0xFF00u) << 8)) : ((f0 & 0x8000u) ? (q.x & 0xFFFFu) : (q.x & 0xFFFFFFu));
+        if (t == 0) { s_head[256] = 0u; s_nlist = 0u; }
+        // exclusive scan over the CTA; the warp totals alternate between two rows, so one barrier is enough
+        // (s_head and s_nlist are visible after it)
+        uint32_t tot = 0u, ex;
+        {
+            const uint32_t inc = warp_incl_scan(cnt);
+            uint32_t *row = s_warp2[parity];
+            if ((t & 31) == 31) row[t >> 5] = inc;
+            __syncthreads();
+            uint32_t base = 0u;
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                const uint32_t x = row[w];
+                if (w < (t >> 5)) base += x;
+                tot += x;
+            }
+            ex = base + inc - cnt;
+        }
         const long long chunk_in = min((long long)kStuffChunk, nbytes - (long long)ch * kStuffChunk);
         const int n_out = (int)chunk_in + (int)tot;
         uint8_t *dst = dst_seg + (long long)ch * kStuffChunk + (OWN_SCAN ? s_prefix[ch] : ffpart[vf * chunks + ch]);
-        // head bytes up to 4-byte alignment, aligned words, tail bytes
-        const int head = min(n_out, (int)((4 - ((uintptr_t)dst & 3)) & 3));
-        if (threadIdx.x < head) dst[threadIdx.x] = s_out[threadIdx.x];
-        const int nwords = (n_out - head) >> 2;
-        uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
-        for (int i = threadIdx.x; i < nwords; i += 256) {
-            const uint8_t *s = s_out + head + 4 * i;
-            dw[i] = (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24);
+        const uint32_t shift = (uint32_t)((uintptr_t)dst & 15u);
+        const uint32_t o = shift + (uint32_t)t * 16u + ex;
+        if (cnt == 0u && t != 0) {
+            const uint32_t skip = (0u - o) & 3u, sh = skip * 8u;     // bytes in front of this piece's first word: its predecessor's
+            const uint32_t nx = s_head[t + 1];
+            uint32_t *w = reinterpret_cast<uint32_t *>(s_out + o + skip);
+            w[0] = __funnelshift_r(q.x, q.y, sh);
+            w[1] = __funnelshift_r(q.y, q.z, sh);
+            w[2] = __funnelshift_r(q.z, q.w, sh);
+            w[3] = __funnelshift_r(q.w, nx, sh);
+        } else {                                                    // (piece 0 has no predecessor to write its first bytes)
+            s_in[t] = q;
+            s_o[t] = (uint16_t)o;
+            s_list[atomicAdd(&s_nlist, 1u)] = (uint16_t)t;
         }
-        const int done = head + 4 * nwords;
-        if (threadIdx.x < n_out - done) dst[done + threadIdx.x] = s_out[done + threadIdx.x];
+        __syncthreads();
+        if (t < (int)s_nlist) {
+            const int p = (int)s_list[t];
+            const uint4 qq = s_in[p];
+            const uint32_t w[4] = {qq.x, qq.y, qq.z, qq.w};
+            uint32_t oo = s_o[p];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const uint8_t b = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
+                s_out[oo++] = b;
+                if (b == 0xFF) s_out[oo++] = 0;
+            }
+            uint32_t nx = s_head[p + 1];
+            while (oo & 3u) {                                       // fill the last word with the successor's first bytes
+                s_out[oo++] = (uint8_t)nx;
+                nx >>= 8;
+            }
+        }
+        __syncthreads();
+        // out: head bytes up to the first 16-byte boundary, whole vectors, tail bytes
+        {
+            const uint32_t end = shift + (uint32_t)n_out;           // staged bytes [shift, end) <-> dst[0, n_out)
+            const uint32_t v0 = (shift + 15u) >> 4, v1 = end >> 4;
+            uint8_t *gbase = dst - shift;
+            for (uint32_t v = v0 + (uint32_t)t; v < v1; v += 256u)
+                *reinterpret_cast<uint4 *>(gbase + 16u * v) = *reinterpret_cast<const uint4 *>(s_out + 16u * v);
+            if (t < 16) {
+                const uint32_t head_end = min(16u * v0, end);
+                if (shift + (uint32_t)t < head_end) gbase[shift + t] = s_out[shift + t];
+                if (v1 >= v0) {
+                    const uint32_t i = 16u * v1 + (uint32_t)t;
+                    if (i < end) gbase[i] = s_out[i];
+                }
+            }
+        }
         // the marker after the segment's last chunk: RSTm (T.81 B.2.4.4 / E.1.4), or EOI after the last segment
         if ((long long)(ch + 1) * kStuffChunk >= nbytes && threadIdx.x == 0) {
             dst[n_out] = 0xFF;
