@@ -275,7 +275,7 @@ int b2j_bitpack(const int16_t *coefs, const uint32_t *offsets, const int64_t *to
                 void *stream);
 
 /* K2 + K3 + K4 fused into one pass over the coefficients (what b2j_encode uses): per chunk of
- * 128 blocks the sizes are counted, scanned inside the CTA, chained across chunks by a
+ * 256 blocks the sizes are counted, scanned inside the CTA, chained across chunks by a
  * decoupled look-back, and the bits are packed at their final offsets; 0xFF stuffing, JFIF
  * header and EOI follow.  Same outputs as b2j_block_bits + b2j_scan + b2j_bitpack.
  * workspace: b2j_entropy_workspace_bytes() bytes, 256-byte aligned. */

@@ -1,6 +1,6 @@
 // Fused single-pass entropy coder (K2 + K3 + K4 packing in one kernel).
 //
-// Persistent CTAs take chunks of 128 consecutive blocks of a stream by ticket (a stream is a frame,
+// Persistent CTAs take chunks of 256 consecutive blocks of a stream by ticket (a stream is a frame,
 // or with [ext] restart intervals one segment of a frame; tickets interleave the streams):
 //   1. the chunk's coefficients (+ 8 lookahead blocks) are loaded once, coalesced, and kept in
 //      shared memory as saturated BYTES (17-word pitch per block: conflict free for the per-thread
@@ -25,7 +25,11 @@
 
 namespace b2j {
 
-constexpr int kChunk = 128;                       // blocks per CTA == threads per CTA
+#ifndef B2J_ENT_CHUNK
+#define B2J_ENT_CHUNK 256
+#endif
+constexpr int kChunk = B2J_ENT_CHUNK;             // blocks per CTA == threads per CTA
+constexpr int kEntWarps = kChunk / 32;
 constexpr int kLookahead = 8;                     // >= 31 bits / (4 bits per smallest block)
 constexpr int kCols = kChunk + kLookahead;        // blocks held in shared memory
 constexpr int kPitch = 17;                        // words per block in shared memory (64 coefficient BYTES + 1 pad)
@@ -43,7 +47,7 @@ constexpr int kSpinLimit = 1 << 22;
 #define B2J_ENT_SMEM_PAD 0
 #endif
 constexpr int kLutWords = 32 + 512 + 4;            // dc[2][16], ac[2][256] (walk layout), zrl_eob[2][2]: gen_huff_lut.py
-constexpr int kFusedSmem = (kCols * kPitch + kCap * kCols + kCols + kCols * 2 + kCols / 2 + kLutWords + 16) * 4 + B2J_ENT_SMEM_PAD;
+constexpr int kFusedSmem = (kCols * kPitch + kCap * kCols + kCols + kCols * 2 + kCols / 2 + kLutWords + 32) * 4 + B2J_ENT_SMEM_PAD;
 
 // The Annex-K code tables in the layout of HuffLut (dc[2][16], ac[2][256]) as a device constant: a CTA copies them with
 // coalesced loads (as a kernel parameter every lane read another word of the constant bank: 11 % of a single frame's time).
@@ -223,7 +227,7 @@ __device__ __forceinline__ void encode_block(uint32_t mlo, uint32_t mhi, int dif
 }
 
 #ifndef B2J_ENT_MIN_CTAS
-#define B2J_ENT_MIN_CTAS 12
+#define B2J_ENT_MIN_CTAS 5
 #endif
 template <bool EAGER, bool SEG>
 __global__ void __launch_bounds__(kChunk, B2J_ENT_MIN_CTAS) k_entropy_fused(const __grid_constant__ FusedEntropyParams P)
@@ -237,7 +241,7 @@ __global__ void __launch_bounds__(kChunk, B2J_ENT_MIN_CTAS) k_entropy_fused(cons
     uint32_t *s_dc = s_mask + kCols * 2 + kCols / 2;         // [2][16]
     uint32_t *s_ac = s_dc + 32;                              // [2][256], the walk's layout
     uint32_t *s_ze = s_ac + 512;                             // [2][2]: ZRL and EOB
-    uint32_t *s_misc = s_ze + 4;                             // warp sums [4], ticket, prefix lo/hi
+    uint32_t *s_misc = s_ze + 4;                             // warp sums [0..15], ticket [16], prefix lo/hi [17..18]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t *my_ovf = P.overflow + (size_t)blockIdx.x * kOvfWords * kCols;
     const unsigned int total_chunks = (unsigned)P.chunks * (unsigned)P.e.n_frames;
@@ -245,9 +249,9 @@ __global__ void __launch_bounds__(kChunk, B2J_ENT_MIN_CTAS) k_entropy_fused(cons
     const unsigned bpm_recip = 65536u / (unsigned)P.e.bpm + 1u;                // n / bpm for n < 4096
   for (;;) {                                                          // persistent: one chunk per ticket
     __syncthreads();                                                  // shared memory of the previous chunk is free
-    if (tid == 0) s_misc[4] = atomicAdd(P.ticket, 1u);
+    if (tid == 0) s_misc[16] = atomicAdd(P.ticket, 1u);
     __syncthreads();
-    const unsigned int id = s_misc[4];
+    const unsigned int id = s_misc[16];
     if (id >= total_chunks) break;
     // tickets interleave the streams: consecutive CTAs work on different streams, so the predecessor
     // chunk of the same stream was started n_frames tickets earlier and has usually published its
@@ -377,7 +381,7 @@ __global__ void __launch_bounds__(kChunk, B2J_ENT_MIN_CTAS) k_entropy_fused(cons
     __syncthreads();
     uint32_t wbase_bits = 0, T = 0;
 #pragma unroll
-    for (int w = 0; w < 4; w++) {
+    for (int w = 0; w < kEntWarps; w++) {
         const uint32_t x = s_misc[w];
         if (w < warp) wbase_bits += x;
         T += x;
@@ -413,12 +417,12 @@ __global__ void __launch_bounds__(kChunk, B2J_ENT_MIN_CTAS) k_entropy_fused(cons
         }
         if (lane == 0) {
             st_volatile(st + ch, kFlagP | (E + (unsigned long long)T));
-            s_misc[5] = (uint32_t)E;
-            s_misc[6] = (uint32_t)(E >> 32);
+            s_misc[17] = (uint32_t)E;
+            s_misc[18] = (uint32_t)(E >> 32);
         }
     }
     __syncthreads();
-    const unsigned long long E = (unsigned long long)s_misc[5] | ((unsigned long long)s_misc[6] << 32);
+    const unsigned long long E = (unsigned long long)s_misc[17] | ((unsigned long long)s_misc[18] << 32);
 
     // ---- 4. compose the owned words.  Bit g of the frame's stream lives in word g >> 5.
     // (bit offsets inside a frame fit 32 bits: make_geo() refuses larger frames)
