@@ -24,7 +24,7 @@ def main():
     ap.add_argument("--restart", type=int, default=0, help="restart interval in MCUs (0 = none)")
     ap.add_argument("--dct", default="model", choices=["model", "fixed"])
     a = ap.parse_args()
-    rgb = lj.read_image(a.src)                                     # PIL on the host, layout conversion on the GPU
+    rgb = lj.read_image(a.src)              # 8-bit grey / RGB / RGBA PNG: decoded on the GPU; other files: PIL on the host
     enc = lj.JpegEncoder(a.sub, quality=a.quality, zrl=a.zrl, restart_interval=a.restart, dct=a.dct,
                          out_cap=rgb.shape[0] * rgb.shape[1] * 4 + 65536)
     jpg = enc.encode(rgb[None])[0]

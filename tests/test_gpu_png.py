@@ -131,3 +131,20 @@ def test_png_to_jpeg_on_the_device(lj):
     frames = lj.decode_png([f])
     out = lj.JpegEncoder("420", quality=75).encode(frames)
     assert out[0] == J.encode_jpeg(a, "420", 75, "eager")
+
+
+def test_batch_transcode_example(lj, tmp_path):
+    """examples/transcode_png_batch.py: a directory of PNG files in, JPEG files out, equal to the oracle's files."""
+    import subprocess
+    from oracle import jpeg_ext as J
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src, dst = tmp_path / "in", tmp_path / "out"
+    src.mkdir()
+    imgs = [photo(48, 80, 3, 20 + i) for i in range(5)]
+    for i, a in enumerate(imgs):
+        (src / ("f%02d.png" % i)).write_bytes(U.write_png(a, filters=[(r + i) % 5 for r in range(48)]))
+    run = subprocess.run([sys.executable, os.path.join(root, "examples", "transcode_png_batch.py"), str(src), str(dst), "--sub", "422",
+                          "--quality", "80", "--batch", "3"], capture_output=True, text=True)
+    assert run.returncode == 0, run.stdout + run.stderr
+    for i, a in enumerate(imgs):
+        assert (dst / ("f%02d.jpg" % i)).read_bytes() == J.encode_jpeg(a, "422", 80, "standard"), i
