@@ -9,8 +9,10 @@
 //      either end of its range sends the walk to the int16 in global memory (L2);
 //   2. every thread takes one block and walks ONLY the set bits of the mask (symbols as in
 //      b2j_entropy.cuh: gateware run-length rules, Annex-K codes), packing the block's bits
-//      MSB-first into a thread-private column of shared memory and counting them;
-//   3. warp-shuffle + CTA exclusive scan of the bit counts; the chunk total is published and
+//      MSB-first into a private column of shared memory and counting them.  Which block a thread
+//      takes follows the blocks' non-zero counts (warp 7 the long ones ... warp 0 the short ones:
+//      "permutation" below), so that the lanes of a warp finish together;
+//   3. exclusive scan of the bit counts in block order (warp 0); the chunk total is published and
 //      the chunk's bit offset inside the frame is obtained by a decoupled look-back over the
 //      chunk totals of its predecessors (one 64-bit status word per chunk: flag | value);
 //   4. every thread composes the 32-bit words of the frame's stream whose first bit lies in
@@ -47,7 +49,12 @@ constexpr int kSpinLimit = 1 << 22;
 #define B2J_ENT_SMEM_PAD 0
 #endif
 constexpr int kLutWords = 32 + 512 + 4;            // dc[2][16], ac[2][256] (walk layout), zrl_eob[2][2]: gen_huff_lut.py
-constexpr int kFusedSmem = (kCols * kPitch + kCap * kCols + kCols + kCols * 2 + kCols / 2 + kLutWords + 32) * 4 + B2J_ENT_SMEM_PAD;
+// Blocks are handed to the walking threads by non-zero count (see "permutation" in the kernel); 0 = thread t walks block t
+#ifndef B2J_ENT_SORT
+#define B2J_ENT_SORT 1
+#endif
+constexpr int kSortWords = B2J_ENT_SORT ? kChunk + kChunk / 2 : 0;   // exclusive bit offsets [kChunk] + permutation [kChunk] (16 bit)
+constexpr int kFusedSmem = (kCols * kPitch + kCap * kCols + kCols + kCols * 2 + kCols / 2 + kLutWords + 32 + kSortWords) * 4 + B2J_ENT_SMEM_PAD;
 
 // The Annex-K code tables in the layout of HuffLut (dc[2][16], ac[2][256]) as a device constant: a CTA copies them with
 // coalesced loads (as a kernel parameter every lane read another word of the constant bank: 11 % of a single frame's time).
@@ -242,6 +249,10 @@ __global__ void __launch_bounds__(kChunk, B2J_ENT_MIN_CTAS) k_entropy_fused(cons
     uint32_t *s_ac = s_dc + 32;                              // [2][256], the walk's layout
     uint32_t *s_ze = s_ac + 512;                             // [2][2]: ZRL and EOB
     uint32_t *s_misc = s_ze + 4;                             // warp sums [0..15], ticket [16], prefix lo/hi [17..18]
+#if B2J_ENT_SORT
+    uint32_t *s_excl = s_misc + 32;                          // [kChunk]: bit offset of every column inside the chunk
+    uint16_t *s_perm = reinterpret_cast<uint16_t *>(s_excl + kChunk);   // [kChunk]: the column thread t walks and composes
+#endif
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t *my_ovf = P.overflow + (size_t)blockIdx.x * kOvfWords * kCols;
     const unsigned int total_chunks = (unsigned)P.chunks * (unsigned)P.e.n_frames;
@@ -286,6 +297,35 @@ __global__ void __launch_bounds__(kChunk, B2J_ENT_MIN_CTAS) k_entropy_fused(cons
 #endif
         // the loads of a batch are issued together: the phase is bound by memory latency (9 dependent round trips
         // per chunk otherwise)
+        auto stage_piece = [&](int i, const uint4 q) {
+            const int b = i >> 3, c = i & 7;
+            // shared memory holds bytes: both halves of a word clamped to -128..127 (packed 16-bit min / max), the low
+            // bytes of the four words gathered by two permutes.  Halving the staging area is what lets 13 instead of 8
+            // CTAs share an SM, and the kernel's speed follows its occupancy (profiles/r02/experiments.txt)
+            uint32_t t0, t1, t2, t3;
+            asm("min.s16x2 %0, %1, %2;" : "=r"(t0) : "r"(q.x), "r"(0x007F007Fu));
+            asm("min.s16x2 %0, %1, %2;" : "=r"(t1) : "r"(q.y), "r"(0x007F007Fu));
+            asm("min.s16x2 %0, %1, %2;" : "=r"(t2) : "r"(q.z), "r"(0x007F007Fu));
+            asm("min.s16x2 %0, %1, %2;" : "=r"(t3) : "r"(q.w), "r"(0x007F007Fu));
+            asm("max.s16x2 %0, %1, %2;" : "=r"(t0) : "r"(t0), "r"(0xFF80FF80u));
+            asm("max.s16x2 %0, %1, %2;" : "=r"(t1) : "r"(t1), "r"(0xFF80FF80u));
+            asm("max.s16x2 %0, %1, %2;" : "=r"(t2) : "r"(t2), "r"(0xFF80FF80u));
+            asm("max.s16x2 %0, %1, %2;" : "=r"(t3) : "r"(t3), "r"(0xFF80FF80u));
+            uint32_t *d = s_coef + b * kPitch + c * 2;
+            d[0] = __byte_perm(t0, t1, 0x6420);
+            d[1] = __byte_perm(t2, t3, 0x6420);
+            if (c == 0) s_dc16[b] = (int16_t)(q.x & 0xFFFFu);
+            // non-zero flags of the eight halves: min(half, 1) per half (one packed instruction per word), the four
+            // words interleaved by multiply-adds: low halves at bits 0, 2, 4, 6, high halves at bits 16, 18, 20, 22
+            uint32_t n0, n1, n2, n3;
+            asm("min.u16x2 %0, %1, %2;" : "=r"(n0) : "r"(q.x), "r"(0x00010001u));
+            asm("min.u16x2 %0, %1, %2;" : "=r"(n1) : "r"(q.y), "r"(0x00010001u));
+            asm("min.u16x2 %0, %1, %2;" : "=r"(n2) : "r"(q.z), "r"(0x00010001u));
+            asm("min.u16x2 %0, %1, %2;" : "=r"(n3) : "r"(q.w), "r"(0x00010001u));
+            const uint32_t mm = n0 + 4u * n1 + 16u * n2 + 64u * n3;
+            const uint32_t m = (mm | (mm >> 15)) & 0xFFu;
+            mask8[b * 8 + c] = (uint8_t)m;
+        };
         for (int i0 = tid; i0 < npieces; i0 += B2J_ENT_LOAD_BATCH * kChunk) {
             uint4 qb[B2J_ENT_LOAD_BATCH];
 #pragma unroll
@@ -295,40 +335,37 @@ __global__ void __launch_bounds__(kChunk, B2J_ENT_MIN_CTAS) k_entropy_fused(cons
             for (int j = 0; j < B2J_ENT_LOAD_BATCH; j++) {
                 const int i = i0 + j * kChunk;
                 if (i >= npieces) break;
-                const int b = i >> 3, c = i & 7;
-                const uint4 q = qb[j];
-                // shared memory holds bytes: both halves of a word clamped to -128..127 (packed 16-bit min / max), the low
-                // bytes of the four words gathered by two permutes.  Halving the staging area is what lets 13 instead of 8
-                // CTAs share an SM, and the kernel's speed follows its occupancy (profiles/r02/experiments.txt)
-                uint32_t t0, t1, t2, t3;
-                asm("min.s16x2 %0, %1, %2;" : "=r"(t0) : "r"(q.x), "r"(0x007F007Fu));
-                asm("min.s16x2 %0, %1, %2;" : "=r"(t1) : "r"(q.y), "r"(0x007F007Fu));
-                asm("min.s16x2 %0, %1, %2;" : "=r"(t2) : "r"(q.z), "r"(0x007F007Fu));
-                asm("min.s16x2 %0, %1, %2;" : "=r"(t3) : "r"(q.w), "r"(0x007F007Fu));
-                asm("max.s16x2 %0, %1, %2;" : "=r"(t0) : "r"(t0), "r"(0xFF80FF80u));
-                asm("max.s16x2 %0, %1, %2;" : "=r"(t1) : "r"(t1), "r"(0xFF80FF80u));
-                asm("max.s16x2 %0, %1, %2;" : "=r"(t2) : "r"(t2), "r"(0xFF80FF80u));
-                asm("max.s16x2 %0, %1, %2;" : "=r"(t3) : "r"(t3), "r"(0xFF80FF80u));
-                uint32_t *d = s_coef + b * kPitch + c * 2;
-                d[0] = __byte_perm(t0, t1, 0x6420);
-                d[1] = __byte_perm(t2, t3, 0x6420);
-                if (c == 0) s_dc16[b] = (int16_t)(q.x & 0xFFFFu);
-                // non-zero flags of the eight halves: min(half, 1) per half (one packed instruction per word), the four
-                // words interleaved by multiply-adds: low halves at bits 0, 2, 4, 6, high halves at bits 16, 18, 20, 22
-                uint32_t n0, n1, n2, n3;
-                asm("min.u16x2 %0, %1, %2;" : "=r"(n0) : "r"(q.x), "r"(0x00010001u));
-                asm("min.u16x2 %0, %1, %2;" : "=r"(n1) : "r"(q.y), "r"(0x00010001u));
-                asm("min.u16x2 %0, %1, %2;" : "=r"(n2) : "r"(q.z), "r"(0x00010001u));
-                asm("min.u16x2 %0, %1, %2;" : "=r"(n3) : "r"(q.w), "r"(0x00010001u));
-                const uint32_t mm = n0 + 4u * n1 + 16u * n2 + 64u * n3;
-                const uint32_t m = (mm | (mm >> 15)) & 0xFFu;
-                mask8[b * 8 + c] = (uint8_t)m;
+                stage_piece(i, qb[j]);
             }
         }
     }
     // k0: position of column 0 inside its MCU
     const int k0 = (int)((unsigned)b0 % (unsigned)e.bpm);
     auto mcu_pos = [&](int col) { const unsigned a = (unsigned)(k0 + col); return (int)(a - ((a * bpm_recip) >> 16) * (unsigned)e.bpm); };
+#if B2J_ENT_SORT
+    // ---- permutation: a warp's time in the walk is that of its longest block, and blocks of very different lengths sit next
+    // to each other (19 of 32 lanes busy when thread t walks block t).  The pieces a warp has just loaded belong to blocks
+    // 32 a + 4 w + k (a = 0..7, k = 0..3): for every k the warp ranks those eight blocks by non-zero count (seven
+    // shuffles, ties by lane), and the block of rank r (0 = longest) goes to thread 32 (7 - r) + 4 w + k: warp 7 walks the
+    // longest block of every group, warp 0 the shortest.  Warp 0 is the one with work after the walk (the lookahead
+    // blocks, the scan, the look-back) while the other warps wait for it, so it gets the light end: with the long blocks
+    // on warp 0 the permutation was 0.87 ms on the headline batch, with the short ones 0.81 (consecutive blocks: 0.89).
+    // The walking thread's lane is still the block's index modulo 32, so the shared-memory bank pattern of the walk is
+    // unchanged.  No barrier of its own (the masks were written by the warp itself) and no CTA-wide sort; columns, bit
+    // counts, the scan and the composition stay in block order.
+    {
+        static_assert(kEntWarps == 8, "the ranking is written for eight warps of 32 blocks");
+        __syncwarp();
+        const int myblk = (lane >> 2) * 32 + warp * 4 + (lane & 3);
+        int key = 0;                                                 // absent blocks of a short chunk rank last
+        if (myblk < nown) key = 1 + __popc(s_mask[myblk * 2] & ~1u) + __popc(s_mask[myblk * 2 + 1]);
+        key = key * 32 + (31 - lane);                                // ties: the lower lane first
+        int r = 0;
+#pragma unroll
+        for (int d = 1; d < 8; d++) r += __shfl_xor_sync(0xFFFFFFFFu, key, 4 * d) > key ? 1 : 0;
+        s_perm[(7 - r) * 32 + warp * 4 + (lane & 3)] = (uint16_t)myblk;
+    }
+#endif
     __syncthreads();
 
     // ---- 2. one walk per block: private packed bits + bit count
@@ -340,11 +377,15 @@ __global__ void __launch_bounds__(kChunk, B2J_ENT_MIN_CTAS) k_entropy_fused(cons
         if (k < e.hv) return k > 0 ? b - 1 : b - e.bpm + e.hv - 1;
         return b - e.bpm;
     };
+#if B2J_ENT_SORT
+    int col = (int)s_perm[tid];                                      // the column this thread walks
+#else
     const int col = tid;                                             // the column this thread walks and composes
+#endif
     PrivSink sink;
     sink.begin(s_priv + col, my_ovf + col);
     int mybits = 0;
-    if (tid < nown) {
+    if (col < nown) {
         const long long b = b0 + col;
         const uint32_t *blk = s_coef + col * kPitch;
         const int k = mcu_pos(col), chroma = k >= e.hv;
@@ -360,6 +401,9 @@ __global__ void __launch_bounds__(kChunk, B2J_ENT_MIN_CTAS) k_entropy_fused(cons
         s_nbits[col] = (uint32_t)bits;
         mybits = bits;
     }
+#if B2J_ENT_SORT
+    else s_nbits[col] = 0u;                                          // (the scan reads every column)
+#endif
     // the lookahead blocks only have to supply the bits that complete this chunk's last word
     if (tid < kLookahead && kChunk + tid < nall && !last) {
         const int colidx = kChunk + tid;
@@ -376,6 +420,34 @@ __global__ void __launch_bounds__(kChunk, B2J_ENT_MIN_CTAS) k_entropy_fused(cons
     }
 
     // ---- 3. CTA exclusive scan of the bit counts
+#if B2J_ENT_SORT
+    // in block order, by warp 0 alone (it also does the look-back): lane l sums columns 8 l .. 8 l + 7
+    __syncthreads();
+    uint32_t T = 0;
+    if (warp == 0) {
+        constexpr int kPer = kChunk / 32;
+        static_assert(kPer % 4 == 0 && 32 % kEntWarps == 0 && (kCap * kCols) % 4 == 0 && (kCols * kPitch) % 4 == 0 && kCols % 4 == 0,
+                      "chunk size / column count do not fit the vector accesses of the scan");
+        uint4 v[kPer / 4];
+#pragma unroll
+        for (int k = 0; k < kPer / 4; k++) v[k] = reinterpret_cast<const uint4 *>(s_nbits + lane * kPer)[k];
+        uint32_t sum = 0u;
+#pragma unroll
+        for (int k = 0; k < kPer / 4; k++) {                         // v becomes the exclusive prefix inside the lane
+            uint32_t x;
+            x = v[k].x; v[k].x = sum; sum += x;
+            x = v[k].y; v[k].y = sum; sum += x;
+            x = v[k].z; v[k].z = sum; sum += x;
+            x = v[k].w; v[k].w = sum; sum += x;
+        }
+        const uint32_t inc = warp_incl_scan(sum);
+        T = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        const uint32_t base = inc - sum;
+#pragma unroll
+        for (int k = 0; k < kPer / 4; k++)
+            reinterpret_cast<uint4 *>(s_excl + lane * kPer)[k] = make_uint4(v[k].x + base, v[k].y + base, v[k].z + base, v[k].w + base);
+    }
+#else
     const uint32_t inc = warp_incl_scan((uint32_t)mybits);
     if (lane == 31) s_misc[warp] = inc;
     __syncthreads();
@@ -387,6 +459,7 @@ __global__ void __launch_bounds__(kChunk, B2J_ENT_MIN_CTAS) k_entropy_fused(cons
         T += x;
     }
     const uint32_t excl = wbase_bits + inc - (uint32_t)mybits;
+#endif
 
     // ---- decoupled look-back over the chunk totals of this frame (warp 0)
     if (warp == 0) {
@@ -431,7 +504,18 @@ __global__ void __launch_bounds__(kChunk, B2J_ENT_MIN_CTAS) k_entropy_fused(cons
     // tail of 4-6 bit blocks can sit entirely inside a word owned by the previous chunk, which
     // sees those blocks as its lookahead columns).
     const bool reaches_end = bl >= nblk;                             // columns 0..nall-1 run to the stream's end
-    if (tid < nown) {
+#if B2J_ENT_SORT
+    // in block order again: the words a warp stores are neighbours in the stream
+    col = tid;
+    if (col < nown) {
+        mybits = (int)s_nbits[col];
+        sink.begin(s_priv + col, my_ovf + col);
+    }
+#endif
+    if (col < nown) {
+#if B2J_ENT_SORT
+        const uint32_t excl = s_excl[col];
+#endif
         const uint32_t total = (uint32_t)mybits;
         if (last && col == nown - 1) P.total_bits[f] = (int64_t)((uint32_t)E + excl + total);
         const uint32_t G = (uint32_t)E + excl;
