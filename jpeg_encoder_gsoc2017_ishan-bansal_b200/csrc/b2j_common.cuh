@@ -56,6 +56,41 @@ static int launch_info(Kernel kernel, int threads, int smem, LaunchInfo *cache /
     return B2J_OK;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// The kernels of one encode follow each other on a stream.  A kernel launched with launch_pdl(..., true, ...) may become
+// resident while its predecessor drains (that one calls pdl_launch_dependents() first thing) and runs its prologue; it must
+// call pdl_wait() before it touches anything the predecessor writes.  Both instructions do nothing in a kernel launched the
+// ordinary way.  One 1080p frame: the launch gaps between K1, the entropy kernel and the stuffing kernel are 10 % of the step.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                     Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
+// The two halves of b2j_entropy_encode for b2j_encode (b2j_entropy_fused.cu): the workspace head (ticket, status words, 0xFF
+// counts) is cleared BEFORE K1 is launched, so that the entropy kernel follows K1 directly on the stream and can be launched
+// as its programmatic dependent.  entropy_try_clear returns false (and does nothing) when the arguments are not valid: the
+// entropy call itself then reports the error.
+bool entropy_try_clear(const b2j_image_desc *desc, int64_t out_cap, int opts, void *workspace, cudaStream_t st);
+int entropy_encode_impl(const int16_t *coefs, const b2j_image_desc *desc, const uint8_t qy_host[64], const uint8_t qc_host[64],
+                        int opts, void *workspace, uint8_t *out, int64_t out_cap, int64_t *sizes, void *stream, bool after_k1);
+
 // ---------------------------------------------------------------- geometry
 struct Geo {
     int width, height;            // source pixels

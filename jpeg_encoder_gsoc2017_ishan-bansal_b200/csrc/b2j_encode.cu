@@ -88,8 +88,10 @@ extern "C" int b2j_encode(const uint8_t *rgb, const b2j_image_desc *desc, int qu
     uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
     int16_t *coefs = reinterpret_cast<int16_t *>(ws + w.coefs);
     const int variant = B2J_FUSED_AUTO | ((zrl & B2J_OPT_DCT_FIXED) ? B2J_FUSED_DCT_FIXED : 0);
+    // the entropy workspace is cleared in front of K1: the three kernels then follow each other directly on the stream
+    const bool cleared = entropy_try_clear(desc, out_cap, zrl & ~B2J_OPT_DCT_FIXED, ws + w.entropy_ws, reinterpret_cast<cudaStream_t>(stream));
     if ((rc = b2j_fused_block(rgb, desc, qy, qc, coefs, variant, stream))) return rc;
-    if ((rc = b2j_entropy_encode(coefs, desc, qy, qc, zrl & ~B2J_OPT_DCT_FIXED, ws + w.entropy_ws, out, out_cap, sizes, stream)))
+    if ((rc = entropy_encode_impl(coefs, desc, qy, qc, zrl & ~B2J_OPT_DCT_FIXED, ws + w.entropy_ws, out, out_cap, sizes, stream, cleared)))
         return rc;
     return B2J_OK;
 }

@@ -312,6 +312,7 @@ __global__ void __launch_bounds__(256, B2J_STUFF_MIN_CTAS) k_stuff_write(const u
     const long long vf = blockIdx.x;
     const long long f = vf / nseg;
     const int seg = (int)(vf % nseg);
+    pdl_wait();                                                     // the packed streams and their sizes are complete
     const long long nbytes = (total_bits[vf] + 7) >> 3;
     if (OWN_SCAN) {
         const int nused = (int)min((long long)chunks, (nbytes + kStuffChunk - 1) / kStuffChunk);
@@ -461,7 +462,7 @@ static int scan_chunks(long long nblk) { return (int)((nblk + kScanChunk - 1) / 
 
 int launch_stuffing(const uint8_t *unstuffed, const int64_t *total_bits, uint32_t *ffpart, int64_t *sizes, uint8_t *out,
                     long long ucap, long long out_cap, int n_frames, const HeaderParam &H, const int *error_flag,
-                    bool counted, cudaStream_t st, int nseg, int rst_phase)
+                    bool counted, cudaStream_t st, int nseg, int rst_phase, bool pdl)
 {
     const int schunks = stuff_chunks(ucap);
     const long long nvf = (long long)n_frames * nseg;
@@ -476,8 +477,11 @@ int launch_stuffing(const uint8_t *unstuffed, const int64_t *total_bits, uint32_
     if (per_seg > schunks) per_seg = schunks;
     if (per_seg < 1) per_seg = 1;
     if (nseg == 1 && (size_t)schunks * sizeof(uint32_t) <= 32768) {
-        k_stuff_write<true><<<dim3((unsigned)nvf, (unsigned)per_seg), 256, (size_t)schunks * sizeof(uint32_t), st>>>(
-            unstuffed, total_bits, ffpart, segbase, sizes, out, ucap, out_cap, schunks, nseg, rst_phase, error_flag, H);
+        // (pdl: launched straight behind the fused entropy kernel, as its programmatic dependent)
+        const cudaError_t le = launch_pdl(k_stuff_write<true>, dim3((unsigned)nvf, (unsigned)per_seg), dim3(256),
+                                          (size_t)schunks * sizeof(uint32_t), st, pdl && counted, unstuffed, total_bits, ffpart, segbase,
+                                          sizes, out, ucap, out_cap, schunks, nseg, rst_phase, error_flag, H);
+        if (le != cudaSuccess) return cuda_fail(le, "k_stuff_write");
     } else {
         k_ff_scan<<<(unsigned)n_frames, 256, 0, st>>>(ffpart, total_bits, segbase, sizes, ucap, out_cap, schunks, nseg, H.len,
                                                       error_flag);

@@ -140,6 +140,6 @@ static inline int stuff_chunks(long long ucap) { return (int)((ucap + kStuffChun
 // are joined with RSTm markers between them, m = (segment + rst_phase) mod 8.
 int launch_stuffing(const uint8_t *unstuffed, const int64_t *total_bits, uint32_t *ffpart, int64_t *sizes, uint8_t *out,
                     long long ucap, long long out_cap, int n_frames, const HeaderParam &H, const int *error_flag,
-                    bool counted, cudaStream_t st, int nseg = 1, int rst_phase = 0);
+                    bool counted, cudaStream_t st, int nseg = 1, int rst_phase = 0, bool pdl = false);
 
 }  // namespace b2j

@@ -256,7 +256,9 @@ __global__ void __launch_bounds__(kChunk, B2J_ENT_MIN_CTAS) k_entropy_fused(cons
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t *my_ovf = P.overflow + (size_t)blockIdx.x * kOvfWords * kCols;
     const unsigned int total_chunks = (unsigned)P.chunks * (unsigned)P.e.n_frames;
+    pdl_launch_dependents();                                                  // (the stuffing kernel's CTAs may queue up)
     for (int i = tid; i < kLutWords; i += kChunk) s_dc[i] = kHuffLutDev[i];   // s_ac and s_ze follow s_dc
+    pdl_wait();                                                               // K1's coefficients are complete and visible
     const unsigned bpm_recip = 65536u / (unsigned)P.e.bpm + 1u;                // n / bpm for n < 4096
   for (;;) {                                                          // persistent: one chunk per ticket
     __syncthreads();                                                  // shared memory of the previous chunk is free
@@ -625,10 +627,31 @@ extern "C" size_t b2j_entropy_workspace_bytes(const b2j_image_desc *desc, int64_
     return b2j_entropy_workspace_bytes_opts(desc, out_cap, 0);
 }
 
+bool b2j::entropy_try_clear(const b2j_image_desc *desc, int64_t out_cap, int opts, void *workspace, cudaStream_t st)
+{
+    Geo g;
+    if (!desc || !workspace || ((uintptr_t)workspace & 255) != 0 || out_cap < kHeaderMax + 2) return false;
+    if ((opts & ~(0xFF | B2J_OPT_RST_PHASE(7) | B2J_OPT_RESTART(0x7FFF))) != 0 || make_geo(desc, &g)) return false;
+    const FusedWs W = fused_ws(g, seg_plan(g, out_cap, opts));
+    if (cudaMemsetAsync(workspace, 0, W.zero_bytes, st) != cudaSuccess) {
+        (void)cudaGetLastError();                                        // the entropy call clears (and reports) itself
+        return false;
+    }
+    return true;
+}
+
 // K2..K4 in one pass over the coefficients: coefs -> JFIF files.
 extern "C" int b2j_entropy_encode(const int16_t *coefs, const b2j_image_desc *desc, const uint8_t qy_host[64],
                                   const uint8_t qc_host[64], int opts, void *workspace, uint8_t *out, int64_t out_cap,
                                   int64_t *sizes, void *stream)
+{
+    return entropy_encode_impl(coefs, desc, qy_host, qc_host, opts, workspace, out, out_cap, sizes, stream, false);
+}
+
+// after_k1: the workspace head was cleared by entropy_try_clear before K1 (the launch in front of this one on the stream).
+int b2j::entropy_encode_impl(const int16_t *coefs, const b2j_image_desc *desc, const uint8_t qy_host[64],
+                             const uint8_t qc_host[64], int opts, void *workspace, uint8_t *out, int64_t out_cap,
+                             int64_t *sizes, void *stream, bool after_k1)
 {
     const int zrl = opts & 0xFF;
     B2J_REQUIRE(coefs && qy_host && qc_host && workspace && out && sizes, B2J_E_ARG, "b2j_entropy_encode: null pointer");
@@ -679,7 +702,7 @@ extern "C" int b2j_entropy_encode(const int16_t *coefs, const b2j_image_desc *de
     static const bool lut_ok = fused_lut_matches_host();
     B2J_REQUIRE(lut_ok, B2J_E_ARG, "b2j_entropy_encode: b2j_huff_lut.inc is not the table the host code derives");
     cudaStream_t st = as_stream(stream);
-    B2J_CUDA(cudaMemsetAsync(ws, 0, status_bytes, st));              // ticket, error flag, chunk status words
+    if (!after_k1) B2J_CUDA(cudaMemsetAsync(ws, 0, status_bytes, st));   // ticket, error flag, chunk status words
     const long long total = (long long)chunks * nvf;
     using Kernel = void (*)(const FusedEntropyParams);
     const bool seg = sp.nseg > 1;
@@ -693,8 +716,10 @@ extern "C" int b2j_entropy_encode(const int16_t *coefs, const b2j_image_desc *de
     long long slots = (long long)li.sms * li.per_sm;
     if (slots > kMaxSlots) slots = kMaxSlots;
     const unsigned grid = (unsigned)(total < slots ? total : slots);   // persistent CTAs, one scratch slot each
-    kernel<<<grid, kChunk, kFusedSmem, st>>>(P);
-    B2J_LAUNCH_CHECK("k_entropy_fused");
+    {
+        const cudaError_t le = launch_pdl(kernel, dim3(grid), dim3(kChunk), (size_t)kFusedSmem, st, after_k1, P);
+        if (le != cudaSuccess) return cuda_fail(le, "k_entropy_fused");
+    }
     return launch_stuffing(P.unstuffed, P.total_bits, ffpart, sizes, out, ucap, out_cap, g.n_frames, H, P.error_flag, true, st,
-                           sp.nseg, (opts >> 12) & 7);
+                           sp.nseg, (opts >> 12) & 7, true);
 }

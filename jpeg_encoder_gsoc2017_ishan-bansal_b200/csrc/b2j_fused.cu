@@ -46,6 +46,7 @@ struct FusedParams {
 template <int H, int V, bool FIXED>
 __global__ void __launch_bounds__(128) k_fused_simple(const __grid_constant__ FusedParams P)
 {
+    pdl_launch_dependents();
     constexpr int BPM = H * V + 2;
     __shared__ uint32_t s_mul[2][64];
     if (threadIdx.x < 128) s_mul[threadIdx.x >> 6][threadIdx.x & 63] = P.qm.mul[threadIdx.x >> 6][threadIdx.x & 63];
@@ -173,6 +174,7 @@ __device__ __forceinline__ TileCoord tile_coord(const FusedParams &P, long long 
 template <int H, int V, bool FIXED>
 __global__ void __launch_bounds__(kThreads, B2J_K1_MIN_CTAS) k_fused_tiled(const __grid_constant__ FusedParams P, long long n_tiles, int tiles_x)
 {
+    pdl_launch_dependents();
     using TS = TileShape<H, V>;
     constexpr int BPM = H * V + 2;
     extern __shared__ __align__(128) uint8_t smem[];

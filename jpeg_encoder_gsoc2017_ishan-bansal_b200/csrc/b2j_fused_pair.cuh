@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(kPairThreads, B2J_PAIR_MIN_CTAS)
 k_fused_pair(const __grid_constant__ FusedParams P, const __grid_constant__ CUtensorMap tmap, unsigned n_regions, int regions_x,
              int kRun)
 {
+    pdl_launch_dependents();                                         // (the entropy kernel's CTAs may queue up behind this grid)
     constexpr int BPP = (LAYOUT == B2J_LAYOUT_RGBA || LAYOUT == B2J_LAYOUT_BGRA) ? 4 : 3;
     constexpr int RO = (LAYOUT == B2J_LAYOUT_BGR || LAYOUT == B2J_LAYOUT_BGRA) ? 2 : 0, BO = 2 - RO;   // byte of r and b in a pixel
     using SS = PairShape<H, V, BPP>;

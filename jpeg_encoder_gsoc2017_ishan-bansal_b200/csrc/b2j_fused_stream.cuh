@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(kStreamThreads, B2J_STREAM_MIN_CTAS)
 k_fused_stream(const __grid_constant__ FusedParams P, const __grid_constant__ CUtensorMap tmap, unsigned n_regions, int regions_x,
                int kRun)
 {
+    pdl_launch_dependents();                                         // (the entropy kernel's CTAs may queue up behind this grid)
     using SS = StreamShape<H, V>;
     constexpr int BPM = H * V + 2;
     extern __shared__ __align__(128) uint8_t smem[];
