@@ -356,16 +356,19 @@ __global__ void __launch_bounds__(kChunk, B2J_ENT_MIN_CTAS) k_entropy_fused(cons
     // unchanged.  No barrier of its own (the masks were written by the warp itself) and no CTA-wide sort; columns, bit
     // counts, the scan and the composition stay in block order.
     {
-        static_assert(kEntWarps == 8, "the ranking is written for eight warps of 32 blocks");
+        static_assert(kEntWarps == 8 || kEntWarps == 4, "the ranking is written for eight or four warps of 32 blocks");
         __syncwarp();
-        const int myblk = (lane >> 2) * 32 + warp * 4 + (lane & 3);
+        // (with four warps a warp's pieces belong to blocks 16 a + 4 w + k: the four blocks of one residue modulo 32 are
+        // those of every other a, and they are ranked among themselves)
+        constexpr int kStep = 32 / kEntWarps;                        // lane distance between two blocks of one group
+        const int myblk = (lane >> 2) * (kChunk / 8) + warp * 4 + (lane & 3);
         int key = 0;                                                 // absent blocks of a short chunk rank last
         if (myblk < nown) key = 1 + __popc(s_mask[myblk * 2] & ~1u) + __popc(s_mask[myblk * 2 + 1]);
         key = key * 32 + (31 - lane);                                // ties: the lower lane first
         int r = 0;
 #pragma unroll
-        for (int d = 1; d < 8; d++) r += __shfl_xor_sync(0xFFFFFFFFu, key, 4 * d) > key ? 1 : 0;
-        s_perm[(7 - r) * 32 + warp * 4 + (lane & 3)] = (uint16_t)myblk;
+        for (int d = 1; d < kEntWarps; d++) r += __shfl_xor_sync(0xFFFFFFFFu, key, kStep * d) > key ? 1 : 0;
+        s_perm[(kEntWarps - 1 - r) * 32 + (myblk & 31)] = (uint16_t)myblk;
     }
 #endif
     __syncthreads();
