@@ -53,6 +53,13 @@ constexpr int kLutWords = 32 + 512 + 4;            // dc[2][16], ac[2][256] (wal
 #ifndef B2J_ENT_SORT
 #define B2J_ENT_SORT 1
 #endif
+#ifndef B2J_ENT_EARLY_LB
+#define B2J_ENT_EARLY_LB 1
+#endif
+#if !B2J_ENT_SORT                                  // (it lives in the permuted kernel's walk-to-scan section)
+#undef B2J_ENT_EARLY_LB
+#define B2J_ENT_EARLY_LB 0
+#endif
 constexpr int kSortWords = B2J_ENT_SORT ? kChunk + kChunk / 2 : 0;   // exclusive bit offsets [kChunk] + permutation [kChunk] (16 bit)
 constexpr int kFusedSmem = (kCols * kPitch + kCap * kCols + kCols + kCols * 2 + kCols / 2 + kLutWords + 32 + kSortWords) * 4 + B2J_ENT_SMEM_PAD;
 
@@ -426,6 +433,15 @@ __global__ void __launch_bounds__(kChunk, B2J_ENT_MIN_CTAS) k_entropy_fused(cons
 
     // ---- 3. CTA exclusive scan of the bit counts
 #if B2J_ENT_SORT
+#if B2J_ENT_EARLY_LB
+    // warp 0 is through with its (short) blocks long before the others: it reads the predecessor chunk's status word now,
+    // so that the L2 round trip runs while it waits at the barrier.  In a batch the predecessor was started n_streams
+    // tickets earlier and has published its inclusive prefix: the look-back behind the barrier then has nothing to wait for
+    // (256 x 1080p: 0.803 -> 0.791 ms).  With few streams the predecessor is still at work and the read would be wasted (one
+    // frame: +0.9 us), so it is only issued when the streams are at least a quarter of the CTAs in flight
+    unsigned long long early = 0ull;
+    if (warp == 0 && ch > 0 && (unsigned)P.e.n_frames * 4u >= gridDim.x) early = ld_volatile(P.status + (long long)f * P.chunks + ch - 1);
+#endif
     // in block order, by warp 0 alone (it also does the look-back): lane l sums columns 8 l .. 8 l + 7
     __syncthreads();
     uint32_t T = 0;
@@ -470,6 +486,10 @@ __global__ void __launch_bounds__(kChunk, B2J_ENT_MIN_CTAS) k_entropy_fused(cons
     if (warp == 0) {
         unsigned long long *st = P.status + (long long)f * P.chunks;
         unsigned long long E = 0;
+#if B2J_ENT_SORT && B2J_ENT_EARLY_LB
+        if ((early >> 62) == 2ull) E = early & kValMask;
+        else
+#endif
         if (ch > 0) {
             if (lane == 0) st_volatile(st + ch, kFlagA | (unsigned long long)T);
             int i = ch - 1;
