@@ -87,3 +87,54 @@ def test_magic_number_conversions():
         t = 36028797018963968.0 + float(int(abs(v) / 8)) * 8        # what RZ(|v| + 2^55) evaluates to
         lo = struct.unpack("<Q", struct.pack("<d", t))[0] & 0xFFFFFFFF
         assert lo == int(abs(v) / 8)
+
+
+def _entropy_walk_permutation(counts, nown, warps=8):
+    """NumPy restatement of the block -> thread assignment of k_entropy_fused (csrc/b2j_entropy_fused.cu, "permutation"):
+    warp w of the CTA has loaded the pieces of blocks (256 / 8 or 128 / 8) * a + 4 w + k, a = 0..7, k = 0..3 (lane = 4 a + k);
+    the blocks of one residue modulo 32 are ranked by non-zero count (ties: lower lane first, absent blocks last) and the
+    block of rank r goes to thread 32 (warps - 1 - r) + residue.  Returns perm[thread] = block."""
+    chunk = 32 * warps
+    step = 32 // warps                       # lane distance between two blocks of one group
+    perm = np.full(chunk, -1, dtype=np.int64)
+    for w in range(warps):
+        lanes = np.arange(32)
+        blk = (lanes >> 2) * (chunk // 8) + w * 4 + (lanes & 3)
+        key = np.where(blk < nown, 1 + counts[np.minimum(blk, chunk - 1)], 0) * 32 + (31 - lanes)
+        for lane in range(32):
+            r = sum(int(key[lane ^ (step * d)] > key[lane]) for d in range(1, warps))
+            t = (warps - 1 - r) * 32 + (blk[lane] & 31)
+            assert perm[t] == -1                      # one block per thread
+            perm[t] = blk[lane]
+    return perm
+
+
+def test_entropy_walk_permutation_properties():
+    """What the kernel's comments claim about the permutation: it is a bijection of the chunk's columns, the walking
+    thread's lane is the block's index modulo 32 (same shared-memory bank pattern as thread t on block t), warp 7 gets
+    the longest and warp 0 the shortest block of every residue class, absent blocks of a short chunk go to the low
+    warps, and the busiest-lane sum over the warps never exceeds that of consecutive blocks."""
+    rng = np.random.default_rng(20171019)
+    for warps in (8, 4):
+        chunk = 32 * warps
+        for trial in range(200):
+            kind = trial % 4
+            if kind == 0:
+                counts = rng.integers(0, 64, chunk)
+            elif kind == 1:
+                counts = rng.integers(0, 4, chunk)                      # many ties
+            elif kind == 2:
+                counts = np.full(chunk, int(rng.integers(0, 64)))       # all equal (grey frames)
+            else:
+                counts = np.minimum(63, rng.geometric(0.12, chunk))     # photo-like: long tail
+            nown = chunk if trial % 3 else int(rng.integers(1, chunk + 1))
+            perm = _entropy_walk_permutation(counts, nown, warps)
+            assert sorted(perm.tolist()) == list(range(chunk))
+            t = np.arange(chunk)
+            assert np.array_equal(perm & 31, t & 31)
+            c = np.where(perm < nown, counts[perm], -1).reshape(warps, 32)  # [warp][lane], -1 = absent
+            assert np.all(np.diff(c, axis=0) >= 0)                      # per residue: counts ascend with the warp index
+            if nown == chunk:
+                new = c.max(axis=1).sum()
+                old = counts.reshape(warps, 32).max(axis=1).sum()
+                assert c[warps - 1].max() == counts.max() and new <= old
